@@ -1,0 +1,128 @@
+"""CPU: the oracle against the golden vectors produced by the real reference
+(oracle/make_golden.py) and against sklearn / closed-form properties."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from music_transcription_b200 import synth
+from oracle import f1 as of1
+from oracle import frontend as ofe
+from oracle import model as omodel
+from oracle import notes as onotes
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "model_*_*.npz"))),
+                         ids=lambda p: os.path.basename(p)[6:-4])
+def test_model_oracle_matches_reference_outputs(path):
+    g = np.load(path)
+    n_mels, H, L, B, T, attn, heads, seed, xseed = [int(v) for v in g["cfg"]]
+    mt = str(g["model_type"])
+    sd = synth.synth_state_dict(mt, n_mels, H, L, seed=seed, use_attention=bool(attn),
+                                use_onset_offset_heads=bool(heads))
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]          # checkpoint key parity
+    x = torch.from_numpy(g["x"])
+    assert torch.equal(x, synth.synth_logmel(B, n_mels, T, seed=xseed))
+    torch.set_num_threads(4)
+    out = omodel.forward(sd, x, mt, H, L, bool(attn), bool(heads), return_all_heads=True)
+    if isinstance(out, dict):
+        for k in ("frame", "onset", "offset"):
+            np.testing.assert_allclose(out[k].numpy(), g[k], atol=2e-5, rtol=0)
+        frame = out["frame"]
+    else:
+        frame = out
+        np.testing.assert_allclose(frame.numpy(), g["frame"], atol=2e-5, rtol=0)
+    assert frame.shape == (B, 88, T)
+    pred = omodel.predict(sd, x, mt, H, L, 0.5, use_attention=bool(attn), use_onset_offset_heads=bool(heads))
+    assert (pred.numpy() != g["pred"]).mean() < 1e-3
+
+
+def test_reference_rejects_zero_length_input():
+    g = np.load(os.path.join(GOLDEN, "model_T0.npz"))
+    assert "Kernel size" in str(g["raised"])      # the T==0 guard of the reference is unreachable
+
+
+def test_notes_oracle_matches_reference_pianoroll_to_midi():
+    g = np.load(os.path.join(GOLDEN, "notes_reference.npz"))
+    fs = 16000 / 512
+    for name in ("random", "sparse", "full", "empty", "edges", "seam"):
+        roll = g[name + "_roll"].astype(np.float32)
+        notes = onotes.group_notes(roll)
+        ev = onotes.notes_to_events(notes, fs)
+        assert len(ev) == len(g[name + "_pitch"]), name
+        if len(ev):
+            assert np.array_equal([e[0] for e in ev], g[name + "_pitch"])
+            assert np.array_equal(np.array([e[1] for e in ev]), g[name + "_start"])   # bit-exact float64
+            assert np.array_equal(np.array([e[2] for e in ev]), g[name + "_end"])
+            assert set(g[name + "_vel"]) == {100}
+    comb = onotes.combine_piano_rolls([g["seam_a"], g["seam_b"]])
+    assert np.array_equal(comb, g["seam_roll"])
+    seam = onotes.group_notes(comb.astype(np.float32))
+    assert any(p == 5 and s == 930 and e == 945 for p, s, e in seam)        # merged across the chunk seam
+
+
+def test_threshold_is_strict_float32_compare():
+    p = np.array([[np.float32(0.1), np.nextafter(np.float32(0.1), np.float32(1))]], dtype=np.float32)
+    assert onotes.threshold_roll(p, 0.1).tolist() == [[0.0, 1.0]]
+    assert (torch.from_numpy(p) > 0.1).float().numpy().tolist() == [[0.0, 1.0]]
+
+
+def test_f1_oracle_matches_reference_evaluate():
+    g = np.load(os.path.join(GOLDEN, "f1_reference.npz"))
+    probs, rolls, lengths = g["probs"], g["rolls"].astype(np.float32), g["lengths"]
+
+    def mean_at(t):
+        return of1.mean_f1(of1.counts_grid(probs, rolls, lengths, [t])[:, 0])
+
+    for t, want in zip(g["at_t"], g["at_f1"]):
+        assert mean_at(float(t)) == pytest.approx(float(want), abs=1e-15)
+    best_t, best_f1, visited = of1.threshold_walk(mean_at)
+    assert best_t == float(g["best_t"]) and best_f1 == pytest.approx(float(g["best_f1"]), abs=1e-15)
+    # default schedule with an interior optimum: 10+9+9+9 thresholds in 4 rounds
+    _, _, v2 = of1.threshold_walk(lambda t: -abs(t - 0.52))
+    assert len(v2) == 37
+
+
+def test_f1_counts_match_sklearn():
+    from sklearn.metrics import confusion_matrix, f1_score
+    for i in range(4):
+        p = synth.planted_probs(88, 64, [0.3, 0.5], seed=i, frac=0.05)
+        y = synth.bernoulli_roll(88, 64, 0.2, seed=i)
+        for t in (0.3, 0.5, 0.999999, 0.0):
+            tp, fp, fn = of1.counts(p, y, 50, t)
+            pred = (torch.from_numpy(p) > t).float().numpy()[:, :50].flatten()
+            cm = confusion_matrix(y[:, :50].flatten(), pred, labels=[0, 1])
+            assert (tp, fp, fn) == (cm[1, 1], cm[0, 1], cm[1, 0])
+            assert of1.f1_from_counts(tp, fp, fn) == pytest.approx(
+                f1_score(y[:, :50].flatten(), pred, zero_division=0), abs=1e-15)
+    assert of1.f1_from_counts(0, 0, 0) == 0.0
+
+
+def test_frontend_oracle_vs_torchaudio_fixture():
+    g = np.load(os.path.join(GOLDEN, "frontend_torchaudio.npz"))
+    y = synth.piano_chord(int(g["k"]), n_samples=int(g["n_samples"]))
+    mine = ofe.logmel(y)
+    assert mine.shape == (320, 1 + int(g["n_samples"]) // 512) and mine.dtype == np.float32
+    np.testing.assert_array_equal(mine, g["logmel_oracle"])          # restatement is deterministic
+    d = np.abs(mine - g["logmel_torchaudio"])
+    assert d.max() < 2e-2 and d.mean() < 2e-4                       # fp32-FFT vs fp64-FFT noise only
+    assert np.abs(mine - ofe.logmel_f64(y)).max() < 1e-4
+
+
+def test_frontend_filterbank_properties():
+    fb = ofe.mel_filterbank()
+    assert fb.shape == (320, 1025) and fb.dtype == np.float32
+    nnz = (fb > 0).sum(1)
+    assert nnz.min() >= 2 and nnz.max() <= 20 and 0.005 < (fb > 0).mean() < 0.007
+    assert abs(float(fb.max()) - 0.1058) < 1e-3
+    # frame count and top_db floor
+    y = synth.piano_chord(1, n_samples=480000)
+    db = ofe.logmel(y)
+    assert db.shape == (320, 938)
+    assert db.min() == pytest.approx(db.max() - 80.0, abs=1e-4) or db.min() > db.max() - 80.0
+    sil = ofe.logmel(np.zeros(48000, np.float32))
+    assert np.all(sil == -100.0)
