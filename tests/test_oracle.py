@@ -125,4 +125,4 @@ def test_frontend_filterbank_properties():
     assert db.shape == (320, 938)
     assert db.min() == pytest.approx(db.max() - 80.0, abs=1e-4) or db.min() > db.max() - 80.0
     sil = ofe.logmel(np.zeros(48000, np.float32))
-    assert np.all(sil == -100.0)
+    assert np.allclose(sil, -100.0, atol=1e-4)        # amin floor, max-80 is below it
