@@ -1,0 +1,159 @@
+/*
+ * amt.h -- C ABI of libamt_sm100.so: the B200 (sm_100a) implementation of the
+ * audio -> piano-roll inference path of cs4247/music-transcription.
+ *
+ * The reference has no FFI layer (it is pure Python); each entry point below
+ * replaces the arithmetic behind one reference call site, cited as file:line
+ * into the reference tree.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative amt_status; it never
+ *     throws or aborts across the boundary.  amt_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ *   - all data pointers are DEVICE pointers unless the name says "host";
+ *     they are borrowed for the duration of the call.  The library allocates
+ *     nothing the caller must free except opaque handles (*_destroy).
+ *   - `stream` is a cudaStream_t passed as void*.  Calls are asynchronous with
+ *     respect to the host unless stated otherwise.
+ *   - there is no CPU fallback: a missing device or a non-sm_100 device is an
+ *     error (AMT_ERR_DEVICE).
+ */
+#ifndef AMT_H_
+#define AMT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* amt_stream_t;
+
+enum amt_status {
+  AMT_OK = 0,
+  AMT_ERR_ARG = -1,       /* bad argument / unsupported configuration (ValueError in Python) */
+  AMT_ERR_DEVICE = -2,    /* no CUDA device, or not compute capability 10.x */
+  AMT_ERR_CUDA = -3,      /* a CUDA runtime / driver call failed */
+  AMT_ERR_STATE = -4,     /* handle not fully initialised (missing weights, ...) */
+  AMT_ERR_WORKSPACE = -5  /* caller-provided workspace too small */
+};
+
+/* ---- library ------------------------------------------------------------ */
+const char* amt_version(void);
+const char* amt_last_error(void);
+/* 0 when the current device can run the kernels (compute capability 10.x). */
+int amt_device_check(void);
+
+/* ---- log-mel frontend --------------------------------------------------- */
+/* Replaces librosa.feature.melspectrogram + librosa.power_to_db as called at
+ * reference main.py:117-125 (and data/dataset.py:155-156,195-196): centred,
+ * zero-padded STFT (periodic Hann, n_fft), |X|^2, slaney mel filterbank
+ * (fmin..fmax, slaney norm), 10*log10(max(1e-10, .)), floor at max-top_db per
+ * chunk. */
+typedef struct amt_frontend amt_frontend;
+int amt_frontend_create(int sr, int n_fft, int hop, int n_mels, double fmin, double fmax,
+                        amt_frontend** out);
+int amt_frontend_destroy(amt_frontend* fe);
+/* 1 + n_samples / hop  (centred STFT frame count; 938 for a 30-s chunk). */
+int amt_frontend_num_frames(const amt_frontend* fe, int n_samples);
+/* Host copy of the (n_mels x (1+n_fft/2)) float32 filterbank, for inspection. */
+int amt_frontend_filterbank_host(const amt_frontend* fe, float* out_host);
+/* wav [B][n_samples] f32 (row stride wav_stride elements) -> out_db [B][n_mels][T] f32.
+ * chunk_max: [B] f32 scratch (device).  top_db < 0 disables the floor. */
+int amt_logmel_f32(amt_frontend* fe, const float* wav, int B, int n_samples, int64_t wav_stride,
+                   float* out_db, float top_db, float* chunk_max, amt_stream_t stream);
+
+/* ---- model forward ------------------------------------------------------ */
+/* Replaces TranscriptionModel.forward -> CNNRNNModel / CNNRNNModelLarge.forward
+ * (reference models/transcription_model.py:91-108, models/cnn_rnn_model.py:57-74
+ * and :262-349), eval mode. */
+enum amt_model_kind { AMT_MODEL_CNN_RNN = 0, AMT_MODEL_CNN_RNN_LARGE = 1 };
+
+typedef struct amt_model_config {
+  int kind;             /* amt_model_kind */
+  int n_mels;
+  int hidden;           /* LSTM hidden size (multiple of 128, <= 768) */
+  int layers;           /* layers of the main BiLSTM */
+  int heads;            /* attention heads (8 in the reference) */
+  int use_attention;    /* large only */
+  int use_onset_offset; /* large only: shared_fc + frame/onset/offset heads */
+} amt_model_config;
+
+typedef struct amt_model amt_model;
+int amt_model_create(const amt_model_config* cfg, amt_model** out);
+int amt_model_destroy(amt_model* m);
+/* Register one packed weight tensor (device pointer, borrowed until destroy or
+ * replacement).  Names and layouts: DESIGN.md "Packed weights";
+ * music_transcription_b200/packing.py produces them from a reference .pth. */
+int amt_model_set_tensor(amt_model* m, const char* name, const void* dev_ptr, size_t nbytes);
+/* Verifies every tensor the configuration needs is present with the right size. */
+int amt_model_finalize(amt_model* m);
+size_t amt_model_workspace_bytes(const amt_model* m, int B, int T);
+/* logmel [B][1][n_mels][T] f32 -> frame/onset/offset logits [B][88][T] f32.
+ * onset/offset may be NULL.  workspace: device scratch of at least
+ * amt_model_workspace_bytes(m,B,T) bytes, 1024-byte aligned. */
+int amt_model_forward(amt_model* m, const float* logmel, int B, int T, float* frame, float* onset,
+                      float* offset, void* workspace, size_t workspace_bytes, amt_stream_t stream);
+
+/* ---- sigmoid / threshold / notes ---------------------------------------- */
+/* probs = sigmoid(logits); roll = (probs > thr) as float {0,1}
+ * (reference main.py:153-156, models/transcription_model.py:263-266).
+ * probs and/or roll may be NULL. */
+int amt_sigmoid_threshold(const float* logits, int64_t n, float thr, float* probs, float* roll,
+                          amt_stream_t stream);
+
+/* Note grouping of reference main.py:204-223 on the roll formed by concatenating
+ * `n_seg` segments along time (main.py:164-186):
+ *   x[p][seg*T + t] = vals[seg*seg_stride + p*pitch_stride + t],  active iff x > thr
+ * (float32 strict compare; pass thr = 0 for an already-binarised roll).
+ * Output rows (pitch_idx, onset_frame, offset_frame), pitch-major then onset
+ * ascending.  notes: int32 [cap][3]; counts: int32 [n_pitch + 1] -- per-pitch
+ * note counts and, last, the total (which may exceed cap: then only the first
+ * `cap` rows were written).  scratch: int32 [n_pitch + 1] device. */
+int amt_threshold_notes(const float* vals, int n_seg, int n_pitch, int T, int64_t seg_stride,
+                        int64_t pitch_stride, float thr, int32_t* notes, int cap, int32_t* counts,
+                        amt_stream_t stream);
+
+/* Framewise TP/FP/FN of reference scripts/evaluate.py:524-553 for every piece
+ * and every threshold in one pass.  probs/target: [n_pieces][n_pitch][T_stride]
+ * f32, only the first lengths[i] frames of piece i count; thresholds: sorted
+ * ascending, float32; out: int64 [n_pieces][n_thr][3] = (TP, FP, FN), overwritten. */
+int amt_f1_counts(const float* probs, const float* target, const int32_t* lengths, int n_pieces,
+                  int n_pitch, int T_stride, const float* thresholds, int n_thr, int64_t* out,
+                  amt_stream_t stream);
+
+/* ---- building blocks exported for tests and profiling ------------------- */
+/* C[M][ldc] (+bias, optional ReLU) = A[M][K] (bf16, row-major) * W[N][K]^T (bf16).
+ * tcgen05/TMA kernel; K % 64 == 0, N % 64 == 0.  out_f32 selects f32 or bf16 output. */
+int amt_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int M, int N, int K,
+                  int ldc, int relu, int out_f32, amt_stream_t stream);
+/* Implicit-GEMM convolution over activations X [B][T][F][Cin] bf16 (Cin % 64 == 0):
+ * Y[B][T][F or F/2][Cout] = act(conv_{kf x kt}(X) (+ 1x1 conv of X2) + bias), optional
+ * 2:1 max-pool over F.  W [Cout][kf*kt*Cin (+Cin2)] bf16 with K index (tap, cin). */
+int amt_conv_bf16(const void* X, const void* X2, const void* W, const float* bias, void* Y, int B, int T,
+                  int F, int Cin, int Cin2, int Cout, int kf, int kt, int relu, int pool,
+                  amt_stream_t stream);
+/* Bidirectional-LSTM recurrence over precomputed input projections; see DESIGN.md. */
+typedef struct amt_lstm_seq {
+  const void* whh;      /* bf16 [4H][H], rows in slice order */
+  const float* gx;      /* f32 [B*T][ld_gx], this sequence's first column */
+  void* out_bf16;       /* bf16 [B*T][ld_out], this sequence's first column (or NULL) */
+  float* out_f32;       /* f32  [B*T][ld_out32] (or NULL) */
+  int H;
+  int reverse;
+  int ld_gx, ld_out, ld_out32;
+} amt_lstm_seq;
+size_t amt_lstm_scratch_bytes(const amt_lstm_seq* seqs, int n_seq, int B);
+int amt_lstm_recurrence(const amt_lstm_seq* seqs_host, int n_seq, int B, int T, void* scratch,
+                        size_t scratch_bytes, amt_stream_t stream);
+/* Clamped softmax attention (reference models/cnn_rnn_model.py:118-139, middle part):
+ * qkv bf16 [B*T][3*D] (q|k|v, each [heads][hd]) -> out bf16 [B*T][D]. */
+int amt_attention_bf16(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip,
+                       amt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMT_H_ */

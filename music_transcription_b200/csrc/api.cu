@@ -1,0 +1,100 @@
+// Library plumbing: error strings, device checks, tensor-map encoding.
+#include "common.cuh"
+
+namespace amt {
+
+char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int g_sms = 0;
+static int g_cc_major = -1;
+
+static int query_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(AMT_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(AMT_ERR_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  }
+  g_sms = prop.multiProcessorCount;
+  g_cc_major = prop.major;
+  return 0;
+}
+
+int ensure_device() {
+  if (g_cc_major < 0) AMT_TRY(query_device());
+  if (g_cc_major != 10)
+    return set_error(AMT_ERR_DEVICE, "libamt_sm100 needs a compute-capability 10.x GPU (B200); found %d.x",
+                     g_cc_major);
+  return 0;
+}
+
+int num_sms() {
+  if (g_cc_major < 0) query_device();
+  return g_sms > 0 ? g_sms : 148;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      cudaGetLastError();
+      return set_error(AMT_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                        const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(AMT_ERR_CUDA,
+                     "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]",
+                     static_cast<int>(r), rank, (unsigned long long)dims[0],
+                     (unsigned long long)(rank > 1 ? dims[1] : 0), (unsigned long long)(rank > 2 ? dims[2] : 0),
+                     (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], rank > 1 ? box[1] : 0,
+                     rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  return 0;
+}
+
+}  // namespace amt
+
+extern "C" {
+
+const char* amt_version(void) { return "amt-sm100 0.1.0"; }
+const char* amt_last_error(void) { return amt::last_error_buf(); }
+int amt_device_check(void) { return amt::ensure_device(); }
+
+}  // extern "C"

@@ -1,0 +1,349 @@
+// Fused log-mel frontend (replaces librosa.feature.melspectrogram + power_to_db as
+// called at reference main.py:117-125): centred zero-padded framing, periodic Hann,
+// real FFT, |X|^2, slaney mel projection, 10*log10, per-chunk (max - top_db) floor.
+//
+// One CTA = 4 warps handles 8 consecutive frames of one chunk.  The samples those
+// frames share (hop 512 / n_fft 2048 = 4x overlap) are staged once in shared memory
+// with coalesced loads; each warp then runs a 1024-point complex FFT of one real
+// 2048-sample frame entirely in registers + one shared-memory transpose
+// (32 lanes x radix-32 in registers, twiddle, transpose, radix-32), recovers the 1025
+// real-FFT bins, and applies the banded (0.6 % dense) mel filterbank as exact fp32
+// dot products.  The complex STFT (7.7 MB/chunk) never exists in HBM.  Results are
+// staged as a [n_mels][8] tile so the (B, n_mels, T) output is written in 32-byte runs.
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace amt {
+
+constexpr int kNfft = 2048;
+constexpr int kHalf = 1024;
+constexpr int kFramesPerCta = 8;
+constexpr int kWarpsPerCta = 4;
+
+struct FrontendDev {
+  const float* window;     // [2048] periodic Hann (fp64 -> fp32)
+  const float2* tw1024;    // [1024] exp(-2*pi*i*k/1024)
+  const float2* tw2048;    // [1025] exp(-2*pi*i*k/2048)
+  const int* fb_start;     // [n_mels] first FFT bin of each filter
+  const int* fb_off;       // [n_mels+1] CSR offsets into fb_w
+  const float* fb_w;       // non-zero weights
+  int n_mels, hop;
+};
+
+// ---- 32-point in-register FFT (radix-2 DIF, output in bit-reversed order) ----
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __constant__ float2 c_tw32[16];   // exp(-2*pi*i*k/32), k = 0..15
+
+template <int N>
+__device__ __forceinline__ void fft_dif_stage(float2 (&v)[32]) {
+  // butterflies of span N/2 inside blocks of N
+#pragma unroll
+  for (int blk = 0; blk < 32; blk += N) {
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+      const float2 a = v[blk + k], b = v[blk + k + N / 2];
+      v[blk + k] = make_float2(a.x + b.x, a.y + b.y);
+      const float2 d = make_float2(a.x - b.x, a.y - b.y);
+      if (k == 0) v[blk + k + N / 2] = d;
+      else if (k * (32 / N) == 8) v[blk + k + N / 2] = make_float2(d.y, -d.x);   // * (-i)
+      else v[blk + k + N / 2] = cmul(d, c_tw32[k * (32 / N)]);
+    }
+  }
+}
+__device__ __forceinline__ void fft32(float2 (&v)[32]) {
+  fft_dif_stage<32>(v);
+  fft_dif_stage<16>(v);
+  fft_dif_stage<8>(v);
+  fft_dif_stage<4>(v);
+  fft_dif_stage<2>(v);
+}
+__host__ __device__ constexpr int bitrev5(int x) {
+  return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  // monotone int encoding: works for mixed signs
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples, int T, FrontendDev fe,
+              float* __restrict__ out, float* __restrict__ chunk_max) {
+  extern __shared__ __align__(16) uint8_t smem_fe[];
+  const int span = (kFramesPerCta - 1) * fe.hop + kNfft;            // samples shared by the CTA's frames
+  float* s_x = reinterpret_cast<float*>(smem_fe);                   // [span]
+  float2* s_z = reinterpret_cast<float2*>(s_x + ((span + 3) & ~3));  // [warps][32*33] transpose / spectrum
+  float* s_p = reinterpret_cast<float*>(s_z + kWarpsPerCta * 32 * 33);   // [warps][1028] power spectrum
+  float* s_out = s_p + kWarpsPerCta * 1028;                         // [n_mels][8]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kFramesPerCta;
+  const float* x = wav + static_cast<long long>(b) * wav_stride;
+
+  // stage samples [t0*hop - 1024, ... + span) with zero padding outside [0, n_samples)
+  const int start = t0 * fe.hop - kHalf;
+  for (int i = tid; i < span; i += blockDim.x) {
+    const int g = start + i;
+    s_x[i] = (g >= 0 && g < n_samples) ? __ldg(x + g) : 0.0f;
+  }
+  __syncthreads();
+
+  float2* zw = s_z + warp * 32 * 33;
+  float* pw = s_p + warp * 1028;
+  float wmax = -INFINITY;
+
+  for (int fi = warp; fi < kFramesPerCta; fi += kWarpsPerCta) {
+    const int t = t0 + fi;
+    if (t < T) {
+      // z[n] = xw[2n] + i xw[2n+1];  n = 32*n1 + n2,  lane = n2, register index = n1
+      float2 v[32];
+      const float* fx = s_x + fi * fe.hop;
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) {
+        const int n = 64 * n1 + 2 * lane;
+        const float2 xs = *reinterpret_cast<const float2*>(fx + n);
+        const float2 w = __ldg(reinterpret_cast<const float2*>(fe.window + n));
+        v[n1] = make_float2(xs.x * w.x, xs.y * w.y);
+      }
+      fft32(v);                                           // over n1 -> k1 (bit-reversed slots)
+      // twiddle W_1024^(n2*k1), then transpose through smem: zw[k1][n2]
+#pragma unroll
+      for (int sidx = 0; sidx < 32; ++sidx) {
+        const int k1 = bitrev5(sidx);
+        const float2 w = __ldg(fe.tw1024 + ((lane * k1) & 1023));
+        zw[k1 * 33 + lane] = cmul(v[sidx], w);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) v[n2] = zw[lane * 33 + n2];      // lane = k1
+      __syncwarp();
+      fft32(v);                                           // over n2 -> k2 ; Z[k1 + 32*k2]
+#pragma unroll
+      for (int sidx = 0; sidx < 32; ++sidx) zw[bitrev5(sidx) * 32 + lane] = v[sidx];   // natural order, k = k1 + 32*k2
+      __syncwarp();
+      // real-FFT recovery: X[k] = E[k] + W_2048^k O[k],  k = 0..1024  (Z[1024] == Z[0])
+      for (int k = lane; k <= kHalf; k += 32) {
+        const float2 a = zw[k & 1023];
+        const float2 c = zw[(kHalf - k) & 1023];
+        const float2 e = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
+        const float2 o = make_float2(0.5f * (a.y + c.y), -0.5f * (a.x - c.x));   // (a - conj(c)) / (2i)
+        const float2 w = __ldg(fe.tw2048 + k);
+        const float2 xk = make_float2(e.x + (o.x * w.x - o.y * w.y), e.y + (o.x * w.y + o.y * w.x));
+        pw[k] = xk.x * xk.x + xk.y * xk.y;
+      }
+      __syncwarp();
+      // banded mel projection + dB
+      for (int m = lane; m < fe.n_mels; m += 32) {
+        const int s = __ldg(fe.fb_start + m), o0 = __ldg(fe.fb_off + m), o1 = __ldg(fe.fb_off + m + 1);
+        float acc = 0.0f;
+        for (int j = o0; j < o1; ++j) acc = fmaf(__ldg(fe.fb_w + j), pw[s + j - o0], acc);
+        const float db = 10.0f * log10f(fmaxf(acc, 1e-10f));
+        s_out[m * kFramesPerCta + fi] = db;
+        wmax = fmaxf(wmax, db);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // coalesced-ish store of the [n_mels][8] tile
+  for (int e = tid; e < fe.n_mels * kFramesPerCta; e += blockDim.x) {
+    const int m = e / kFramesPerCta, fi = e - m * kFramesPerCta;
+    if (t0 + fi < T) out[(static_cast<long long>(b) * fe.n_mels + m) * T + t0 + fi] = s_out[e];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+  if (lane == 0 && wmax > -INFINITY) atomic_max_float(chunk_max + b, wmax);
+}
+
+__global__ void fill_kernel(float* p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void topdb_floor_kernel(float* __restrict__ x, const float* __restrict__ chunk_max, long long per_chunk,
+                                   float top_db, int vec) {
+  const int b = blockIdx.y;
+  const float floor_v = chunk_max[b] - top_db;
+  float* xb = x + b * per_chunk;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (vec) {   // per_chunk % 4 == 0 and 16-byte aligned base
+    float4* p = reinterpret_cast<float4*>(xb);
+    for (long long i = i0; i < (per_chunk >> 2); i += stride) {
+      float4 v = p[i];
+      v.x = fmaxf(v.x, floor_v); v.y = fmaxf(v.y, floor_v); v.z = fmaxf(v.z, floor_v); v.w = fmaxf(v.w, floor_v);
+      p[i] = v;
+    }
+  } else {
+    for (long long i = i0; i < per_chunk; i += stride) xb[i] = fmaxf(xb[i], floor_v);
+  }
+}
+
+}  // namespace amt
+
+// ----------------------------------------------------------------------------
+// host: filterbank / tables (float64, following SURVEY.md Appendix A)
+// ----------------------------------------------------------------------------
+struct amt_frontend {
+  int sr, n_fft, hop, n_mels;
+  std::vector<float> fb_dense;   // n_mels x (1 + n_fft/2)
+  amt::FrontendDev dev;
+  void* dev_blob;
+  int max_band;
+};
+
+namespace {
+
+double hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+double mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+}  // namespace
+
+extern "C" {
+
+int amt_frontend_create(int sr, int n_fft, int hop, int n_mels, double fmin, double fmax, amt_frontend** out) {
+  using namespace amt;
+  AMT_REQUIRE(out != nullptr, "frontend: out is NULL");
+  AMT_REQUIRE(n_fft == kNfft, "frontend: n_fft must be 2048 (librosa default used by the reference), got %d", n_fft);
+  AMT_REQUIRE(hop > 0 && hop <= 1024 && hop % 2 == 0, "frontend: hop must be even and in (0, 1024], got %d", hop);
+  AMT_REQUIRE(n_mels > 0 && n_mels <= 1024 && sr > 0, "frontend: bad n_mels / sr");
+  if (fmax <= 0) fmax = sr / 2.0;
+  AMT_TRY(ensure_device());
+  const int bins = 1 + n_fft / 2;
+  auto* fe = new amt_frontend();
+  fe->sr = sr; fe->n_fft = n_fft; fe->hop = hop; fe->n_mels = n_mels;
+  fe->fb_dense.assign(static_cast<size_t>(n_mels) * bins, 0.0f);
+  // mel points (np.linspace semantics) and triangular slaney-normalised filters
+  std::vector<double> mel_f(n_mels + 2);
+  const double m0 = hz_to_mel(fmin), m1 = hz_to_mel(fmax);
+  for (int i = 0; i < n_mels + 2; ++i) {
+    const double step = (m1 - m0) / (n_mels + 1);
+    mel_f[i] = mel_to_hz(i == n_mels + 1 ? m1 : m0 + step * i);
+  }
+  std::vector<int> start(n_mels), off(n_mels + 1, 0);
+  std::vector<float> w;
+  int max_band = 0;
+  for (int i = 0; i < n_mels; ++i) {
+    const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+    const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+    int first = -1, last = -1;
+    for (int k = 0; k < bins; ++k) {
+      const double fk = static_cast<double>(k) * (static_cast<double>(sr) / n_fft);
+      const double lower = -(mel_f[i] - fk) / fd0, upper = (mel_f[i + 2] - fk) / fd1;
+      const double v = std::max(0.0, std::min(lower, upper)) * enorm;
+      const float vf = static_cast<float>(v);
+      fe->fb_dense[static_cast<size_t>(i) * bins + k] = vf;
+      if (vf > 0.0f) { if (first < 0) first = k; last = k; }
+    }
+    start[i] = first < 0 ? 0 : first;
+    const int cnt = first < 0 ? 0 : last - first + 1;
+    for (int k = 0; k < cnt; ++k) w.push_back(fe->fb_dense[static_cast<size_t>(i) * bins + first + k]);
+    off[i + 1] = off[i] + cnt;
+    max_band = std::max(max_band, cnt);
+  }
+  fe->max_band = max_band;
+  // tables
+  std::vector<float> window(kNfft);
+  std::vector<float2> tw1024(1024), tw2048(1025);
+  const double PI = 3.14159265358979323846;
+  for (int n = 0; n < kNfft; ++n) window[n] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * PI * n / kNfft));
+  for (int k = 0; k < 1024; ++k) tw1024[k] = make_float2((float)std::cos(2.0 * PI * k / 1024.0), (float)-std::sin(2.0 * PI * k / 1024.0));
+  for (int k = 0; k <= 1024; ++k) tw2048[k] = make_float2((float)std::cos(2.0 * PI * k / 2048.0), (float)-std::sin(2.0 * PI * k / 2048.0));
+  float2 tw32[16];
+  for (int k = 0; k < 16; ++k) tw32[k] = make_float2((float)std::cos(2.0 * PI * k / 32.0), (float)-std::sin(2.0 * PI * k / 32.0));
+  cudaError_t ce = cudaMemcpyToSymbol(c_tw32, tw32, sizeof(tw32));
+  if (ce != cudaSuccess) { delete fe; return set_error(AMT_ERR_CUDA, "frontend: constant upload failed: %s", cudaGetErrorString(ce)); }
+
+  // one device blob
+  size_t o_win = 0, o_t1 = o_win + sizeof(float) * kNfft, o_t2 = o_t1 + sizeof(float2) * 1024,
+         o_st = o_t2 + sizeof(float2) * 1025 + 8, o_off = o_st + sizeof(int) * n_mels,
+         o_w = align_up(o_off + sizeof(int) * (n_mels + 1), 16), total = o_w + sizeof(float) * (w.size() + 1);
+  std::vector<uint8_t> blob(total, 0);
+  memcpy(blob.data() + o_win, window.data(), sizeof(float) * kNfft);
+  memcpy(blob.data() + o_t1, tw1024.data(), sizeof(float2) * 1024);
+  memcpy(blob.data() + o_t2, tw2048.data(), sizeof(float2) * 1025);
+  memcpy(blob.data() + o_st, start.data(), sizeof(int) * n_mels);
+  memcpy(blob.data() + o_off, off.data(), sizeof(int) * (n_mels + 1));
+  if (!w.empty()) memcpy(blob.data() + o_w, w.data(), sizeof(float) * w.size());
+  void* d = nullptr;
+  ce = cudaMalloc(&d, total);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d, blob.data(), total, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { if (d) cudaFree(d); delete fe; return set_error(AMT_ERR_CUDA, "frontend: table upload failed: %s", cudaGetErrorString(ce)); }
+  uint8_t* db = static_cast<uint8_t*>(d);
+  fe->dev_blob = d;
+  fe->dev.window = reinterpret_cast<const float*>(db + o_win);
+  fe->dev.tw1024 = reinterpret_cast<const float2*>(db + o_t1);
+  fe->dev.tw2048 = reinterpret_cast<const float2*>(db + o_t2);
+  fe->dev.fb_start = reinterpret_cast<const int*>(db + o_st);
+  fe->dev.fb_off = reinterpret_cast<const int*>(db + o_off);
+  fe->dev.fb_w = reinterpret_cast<const float*>(db + o_w);
+  fe->dev.n_mels = n_mels;
+  fe->dev.hop = hop;
+  *out = fe;
+  return 0;
+}
+
+int amt_frontend_destroy(amt_frontend* fe) {
+  if (!fe) return 0;
+  if (fe->dev_blob) cudaFree(fe->dev_blob);
+  delete fe;
+  return 0;
+}
+
+int amt_frontend_num_frames(const amt_frontend* fe, int n_samples) {
+  if (!fe || n_samples < 0) return amt::set_error(AMT_ERR_ARG, "frontend: bad arguments");
+  return 1 + n_samples / fe->hop;
+}
+
+int amt_frontend_filterbank_host(const amt_frontend* fe, float* out_host) {
+  if (!fe || !out_host) return amt::set_error(AMT_ERR_ARG, "frontend: bad arguments");
+  memcpy(out_host, fe->fb_dense.data(), fe->fb_dense.size() * sizeof(float));
+  return 0;
+}
+
+int amt_logmel_f32(amt_frontend* fe, const float* wav, int B, int n_samples, int64_t wav_stride, float* out_db,
+                   float top_db, float* chunk_max, amt_stream_t stream_) {
+  using namespace amt;
+  AMT_REQUIRE(fe && wav && out_db && chunk_max, "logmel: NULL argument");
+  AMT_REQUIRE(B > 0 && n_samples > 0 && wav_stride >= n_samples, "logmel: bad sizes");
+  AMT_TRY(ensure_device());
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int T = 1 + n_samples / fe->hop;
+  const int span = (kFramesPerCta - 1) * fe->hop + kNfft;
+  const size_t smem = sizeof(float) * ((span + 3) & ~3) + sizeof(float2) * kWarpsPerCta * 32 * 33 +
+                      sizeof(float) * kWarpsPerCta * 1028 + sizeof(float) * fe->n_mels * kFramesPerCta;
+  static size_t attr = 0;
+  if (smem > attr) {
+    AMT_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  fill_kernel<<<ceil_div(B, 256), 256, 0, stream>>>(chunk_max, B, -INFINITY);
+  AMT_CHECK_LAUNCH();
+  dim3 grid(ceil_div(T, kFramesPerCta), B);
+  AMT_REQUIRE(B <= 65535, "logmel: B must be <= 65535");
+  logmel_kernel<<<grid, kWarpsPerCta * 32, smem, stream>>>(wav, wav_stride, n_samples, T, fe->dev, out_db, chunk_max);
+  AMT_CHECK_LAUNCH();
+  if (top_db >= 0.0f) {
+    const long long per_chunk = static_cast<long long>(fe->n_mels) * T;
+    const int vec = (per_chunk % 4 == 0) && (reinterpret_cast<uintptr_t>(out_db) % 16 == 0);
+    const long long work = vec ? per_chunk / 4 : per_chunk;
+    dim3 g2(static_cast<unsigned>(std::min<long long>((work + 255) / 256, 64)), B);
+    topdb_floor_kernel<<<g2, 256, 0, stream>>>(out_db, chunk_max, per_chunk, top_db, vec);
+    AMT_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// Internal (non-ABI) launch entry points shared between translation units.
+#pragma once
+#include "common.cuh"
+
+namespace amt {
+
+struct ConvGemmDesc {
+  const void* X;  int C;            // primary activations [B][T][F][C] bf16
+  const void* X2; int C2;           // optional second source (1x1, centre tap) or nullptr
+  int B, T, F;
+  const void* W;                    // [N][Ktot] bf16, Ktot = kf*kt*C + C2, K index = (tap, channel)
+  const float* bias;                // [N]
+  int N;
+  int kf, kt;
+  void* out; long long ld_out;
+  int relu, pool, out_f32;
+  int boxF, boxT;                   // M tile = boxF x boxT positions (= 128)
+};
+
+int run_conv_gemm(const ConvGemmDesc& d, cudaStream_t stream);
+int run_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, long long ldc, int relu,
+             int out_f32, cudaStream_t stream);
+int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+size_t lstm_scratch_bytes(const amt_lstm_seq* seqs, int n_seq, int B);
+int run_attention(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip, cudaStream_t stream);
+int run_conv1(const float* x, const float* w, const float* bias, void* out, int B, int Fin, int T, cudaStream_t stream);
+int run_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, void* out, long long rows,
+                      int D, float eps, cudaStream_t stream);
+int run_heads_transpose(const float* in, int ld, int B, int T, int n_heads, float* o0, float* o1, float* o2,
+                        cudaStream_t stream);
+
+}  // namespace amt

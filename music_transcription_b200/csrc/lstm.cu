@@ -1,0 +1,326 @@
+// Persistent LSTM recurrence for sm_100a (nn.LSTM eval forward, gate order i,f,g,o;
+// reference models/cnn_rnn_model.py:45-52,69-70 and :212-228,309-312).
+//
+// The input projections x_t * W_ih^T + b_ih + b_hh are precomputed for all t by the
+// tcgen05 GEMM (tc_gemm.cu); this kernel runs only the T dependent steps
+//     gates = gx[t] + h_{t-1} * W_hh^T ;  c' = s(f) c + s(i) tanh(g) ;  h' = s(o) tanh(c')
+// for several independent sequences at once (forward / reverse directions, the main
+// and the local LSTM, and groups of BC chunks).
+//
+// Decomposition: one CTA per (batch group, sequence, slice of 32 hidden units).  The
+// CTA keeps its 128 x H slice of W_hh (4 gates x 32 units, bf16) resident in shared
+// memory for all T steps as the K-major swizzled A operand of tcgen05.mma; per step
+// it gathers h_{t-1} (BC x H bf16, published by the sibling slices through L2) as the
+// B operand, issues H/16 MMAs into a 128 x BC fp32 TMEM accumulator, and finishes the
+// cell update in registers (cell state never leaves the SM, fp32).  Slices of one
+// sequence synchronise per step through a release/acquire counter in global memory;
+// the launch is cooperative so all CTAs are co-resident.
+#include <cooperative_groups.h>
+
+#include "kernels.cuh"
+
+namespace amt {
+
+constexpr int kMaxSeq = 8;
+
+struct LstmSeqDev {
+  const __nv_bfloat16* whh;
+  const float* gx;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  int H, reverse, ld_gx, ld_out, ld_out32, n_slices, cta_begin;
+};
+
+struct LstmParams {
+  LstmSeqDev seq[kMaxSeq];
+  int n_seq, ctas_per_group, B, T, n_groups, Hmax;
+  __nv_bfloat16* hbuf;   // [n_groups][n_seq][2][BC][Hmax]
+  uint32_t* flags;       // [n_groups][n_seq]
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+template <int BC>
+__global__ void __launch_bounds__(128, 1) lstm_recurrence_kernel(const LstmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int group = blockIdx.x / p.ctas_per_group;
+  const int within = blockIdx.x - group * p.ctas_per_group;
+  int q = 0;
+  for (int i = 1; i < p.n_seq; ++i)
+    if (within >= p.seq[i].cta_begin) q = i;
+  const LstmSeqDev sq = p.seq[q];
+  const int slice = within - sq.cta_begin;
+  const int H = sq.H;
+  const int kblocks = H >> 6;
+
+  uint8_t* w_smem = smem;                                       // kblocks x 16 KB
+  uint8_t* h_smem = w_smem + kblocks * 16384;                   // kblocks x BC*128 B
+  float* xch = reinterpret_cast<float*>(h_smem + kblocks * BC * 128);   // [128][17]
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(xch + 128 * 17);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+  // ---- one-time setup: barrier, TMEM, resident W_hh slice ----
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_init(mma_bar, 1);
+      ptx::mbar_fence_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, BC < 32 ? 32 : BC);
+    ptx::tmem_relinquish();
+  }
+  {
+    const int chunks_per_row = H >> 3;
+    const uint4* src = reinterpret_cast<const uint4*>(sq.whh + static_cast<size_t>(slice) * 128 * H);
+    for (int e = tid; e < 128 * chunks_per_row; e += 128) {
+      const int row = e / chunks_per_row;
+      const int cc = e - row * chunks_per_row;
+      *reinterpret_cast<uint4*>(w_smem + (cc >> 3) * 16384 + ptx::sw128_offset(row, cc & 7)) = __ldg(src + e);
+    }
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int b0 = group * BC;                       // first chunk of this batch group
+  const int nvalid = min(BC, p.B - b0);            // chunks >= nvalid are padding
+  const int r = tid;                               // gate row inside the slice: 4*unit_local + gate
+  const int gate = lane & 3;
+  const int unit = slice * 32 + (r >> 2);          // hidden unit this thread updates
+  const int jlane = lane & 3;                      // batch sub-column this thread updates
+  // activation as a*sigmoid(k*x)+c: tanh(x) = 2*sigmoid(2x)-1 for the g gate
+  const float act_k = gate == 2 ? 2.0f : 1.0f;
+  const float act_a = gate == 2 ? 2.0f : 1.0f;
+  const float act_c = gate == 2 ? -1.0f : 0.0f;
+
+  __nv_bfloat16* hbuf = p.hbuf + static_cast<size_t>(group * p.n_seq + q) * 2 * BC * p.Hmax;
+  uint32_t* flag = p.flags + group * p.n_seq + q;
+  const float* gx_row = sq.gx + slice * 128 + r;
+  constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BC);
+
+  float cstate[BC / 4];
+#pragma unroll
+  for (int i = 0; i < BC / 4; ++i) cstate[i] = 0.0f;
+  uint32_t parity = 0;
+
+  for (int step = 0; step < p.T; ++step) {
+    const int t = sq.reverse ? p.T - 1 - step : step;
+
+    // prefetch this step's input projections (independent of h_{t-1})
+    float gxv[BC];
+#pragma unroll
+    for (int b = 0; b < BC; ++b)
+      gxv[b] = b < nvalid ? __ldg(gx_row + (static_cast<size_t>(b0 + b) * p.T + t) * sq.ld_gx) : 0.0f;
+
+    if (step > 0) {
+      if (tid == 0) {
+        const uint32_t target = static_cast<uint32_t>(step) * sq.n_slices;
+        while (ptx::ld_acquire_gpu(flag) < target) {
+        }
+      }
+      __syncthreads();
+      // gather h_{t-1} (BC x H bf16) from L2 into the swizzled B-operand tile
+      const uint4* hsrc = reinterpret_cast<const uint4*>(hbuf + static_cast<size_t>((step - 1) & 1) * BC * p.Hmax);
+      const int chunks_per_row = H >> 3;
+      for (int e = tid; e < BC * chunks_per_row; e += 128) {
+        const int row = e / chunks_per_row;
+        const int cc = e - row * chunks_per_row;
+        const uint4 v = ptx::ld_cg_v4(hsrc + static_cast<size_t>(row) * (p.Hmax >> 3) + cc);
+        *reinterpret_cast<uint4*>(h_smem + (cc >> 3) * (BC * 128) + ptx::sw128_offset(row, cc & 7)) = v;
+      }
+      ptx::fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        ptx::tc_fence_after();
+        const uint32_t wa = ptx::smem_u32(w_smem);
+        const uint32_t ha = ptx::smem_u32(h_smem);
+        for (int kb = 0; kb < kblocks; ++kb) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_ss(tmem_base, ptx::umma_desc_sw128(wa + kb * 16384 + k * 32),
+                              ptx::umma_desc_sw128(ha + kb * (BC * 128) + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(mma_bar);
+      }
+      ptx::mbar_wait(mma_bar, parity);
+      parity ^= 1;
+      ptx::tc_fence_after();
+    }
+
+    __nv_bfloat16* hdst = hbuf + static_cast<size_t>(step & 1) * BC * p.Hmax;
+#pragma unroll
+    for (int cc = 0; cc < BC / 16; ++cc) {
+      uint32_t v[16];
+      if (step > 0) {
+        ptx::tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + cc * 16, v);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float pre = __uint_as_float(v[j]) + gxv[cc * 16 + j];
+        xch[r * 17 + j] = act_a * sigmoidf_(act_k * pre) + act_c;
+      }
+      __syncwarp();
+      const float* g4 = xch + (r & ~3) * 17;      // rows of this thread's unit: i, f, g, o
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int j = jlane + 4 * m;
+        const float gi = g4[j], gf = g4[17 + j], gg = g4[34 + j], go = g4[51 + j];
+        const float c = gf * cstate[cc * 4 + m] + gi * gg;
+        cstate[cc * 4 + m] = c;
+        const float h = go * (2.0f * sigmoidf_(2.0f * c) - 1.0f);
+        const int b = cc * 16 + j;
+        const __nv_bfloat16 hb = __float2bfloat16_rn(h);
+        hdst[static_cast<size_t>(b) * p.Hmax + unit] = hb;
+        if (b < nvalid) {
+          const size_t row = static_cast<size_t>(b0 + b) * p.T + t;
+          if (sq.out_bf16) sq.out_bf16[row * sq.ld_out + unit] = hb;
+          if (sq.out_f32) sq.out_f32[row * sq.ld_out32 + unit] = h;
+        }
+      }
+      __syncwarp();
+    }
+
+    // publish h_t to the sibling slices
+    ptx::tc_fence_before();
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) ptx::red_release_gpu_add(flag, 1u);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, BC < 32 ? 32 : BC);
+  }
+}
+
+static size_t lstm_smem_bytes(int Hmax, int BC) {
+  return static_cast<size_t>(Hmax / 64) * 16384 + static_cast<size_t>(Hmax / 64) * BC * 128 + 128 * 17 * 4 + 64 + 1024;
+}
+
+struct LstmPlan {
+  int BC, n_groups, ctas_per_group, Hmax;
+  size_t flags_bytes, hbuf_bytes;
+};
+
+static int lstm_plan(const amt_lstm_seq* seqs, int n_seq, int B, LstmPlan* plan) {
+  AMT_REQUIRE(n_seq >= 1 && n_seq <= kMaxSeq, "lstm: n_seq must be in 1..%d", kMaxSeq);
+  AMT_REQUIRE(B >= 1, "lstm: empty batch");
+  int ctas = 0, Hmax = 0;
+  for (int i = 0; i < n_seq; ++i) {
+    AMT_REQUIRE(seqs[i].H % 64 == 0 && seqs[i].H >= 64 && seqs[i].H <= 768, "lstm: hidden size %d unsupported (multiple of 64, <= 768)",
+                seqs[i].H);
+    ctas += seqs[i].H / 32;
+    Hmax = seqs[i].H > Hmax ? seqs[i].H : Hmax;
+  }
+  const int sms = num_sms();
+  AMT_REQUIRE(ctas <= sms, "lstm: %d CTAs per batch group exceed the %d SMs", ctas, sms);
+  const int max_groups = sms / ctas;
+  int BC = 0;
+  for (int cand : {16, 32, 64}) {
+    if (lstm_smem_bytes(Hmax, cand) > 227 * 1024) break;
+    BC = cand;
+    if (ceil_div(B, cand) <= max_groups) break;
+  }
+  AMT_REQUIRE(BC > 0, "lstm: hidden size %d does not fit in shared memory", Hmax);
+  plan->BC = BC;
+  plan->n_groups = ceil_div(B, BC) < max_groups ? ceil_div(B, BC) : max_groups;   // per launch
+  plan->ctas_per_group = ctas;
+  plan->Hmax = Hmax;
+  plan->flags_bytes = align_up(static_cast<size_t>(plan->n_groups) * n_seq * 4, 256);
+  plan->hbuf_bytes = static_cast<size_t>(plan->n_groups) * n_seq * 2 * BC * Hmax * 2;
+  return 0;
+}
+
+template <int BC>
+static int lstm_launch(const LstmParams& p, int grid, size_t smem, cudaStream_t stream) {
+  static size_t attr = 0;
+  if (smem > attr) {
+    AMT_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  void* args[] = {const_cast<LstmParams*>(&p)};
+  AMT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_recurrence_kernel<BC>), dim3(grid), dim3(128), args,
+                                       smem, stream));
+  return 0;
+}
+
+int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, size_t scratch_bytes,
+             cudaStream_t stream) {
+  AMT_TRY(ensure_device());
+  LstmPlan plan;
+  AMT_TRY(lstm_plan(seqs, n_seq, B, &plan));
+  AMT_REQUIRE(T >= 1, "lstm: T must be >= 1");
+  if (scratch_bytes < plan.flags_bytes + plan.hbuf_bytes)
+    return set_error(AMT_ERR_WORKSPACE, "lstm: scratch %zu < %zu bytes", scratch_bytes, plan.flags_bytes + plan.hbuf_bytes);
+  const int per_launch = plan.n_groups * plan.BC;
+  for (int bstart = 0; bstart < B; bstart += per_launch) {
+    const int Bl = B - bstart < per_launch ? B - bstart : per_launch;
+    LstmParams p{};
+    int begin = 0;
+    for (int i = 0; i < n_seq; ++i) {
+      LstmSeqDev& s = p.seq[i];
+      const size_t row0 = static_cast<size_t>(bstart) * T;
+      s.whh = static_cast<const __nv_bfloat16*>(seqs[i].whh);
+      s.gx = seqs[i].gx + row0 * seqs[i].ld_gx;
+      s.out_bf16 = seqs[i].out_bf16 ? static_cast<__nv_bfloat16*>(seqs[i].out_bf16) + row0 * seqs[i].ld_out : nullptr;
+      s.out_f32 = seqs[i].out_f32 ? seqs[i].out_f32 + row0 * seqs[i].ld_out32 : nullptr;
+      s.H = seqs[i].H;
+      s.reverse = seqs[i].reverse;
+      s.ld_gx = seqs[i].ld_gx;
+      s.ld_out = seqs[i].ld_out;
+      s.ld_out32 = seqs[i].ld_out32;
+      s.n_slices = seqs[i].H / 32;
+      s.cta_begin = begin;
+      begin += s.n_slices;
+    }
+    p.n_seq = n_seq;
+    p.ctas_per_group = plan.ctas_per_group;
+    p.B = Bl;
+    p.T = T;
+    p.n_groups = ceil_div(Bl, plan.BC);
+    p.Hmax = plan.Hmax;
+    p.flags = static_cast<uint32_t*>(scratch);
+    p.hbuf = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(scratch) + plan.flags_bytes);
+    AMT_CUDA(cudaMemsetAsync(p.flags, 0, plan.flags_bytes, stream));
+    const int grid = p.n_groups * plan.ctas_per_group;
+    const size_t smem = lstm_smem_bytes(plan.Hmax, plan.BC);
+    if (plan.BC == 16) AMT_TRY(lstm_launch<16>(p, grid, smem, stream));
+    else if (plan.BC == 32) AMT_TRY(lstm_launch<32>(p, grid, smem, stream));
+    else AMT_TRY(lstm_launch<64>(p, grid, smem, stream));
+  }
+  return 0;
+}
+
+size_t lstm_scratch_bytes(const amt_lstm_seq* seqs, int n_seq, int B) {
+  LstmPlan plan;
+  if (lstm_plan(seqs, n_seq, B, &plan) != 0) return 0;
+  return plan.flags_bytes + plan.hbuf_bytes;
+}
+
+}  // namespace amt
+
+extern "C" {
+
+size_t amt_lstm_scratch_bytes(const amt_lstm_seq* seqs, int n_seq, int B) {
+  return amt::lstm_scratch_bytes(seqs, n_seq, B);
+}
+
+int amt_lstm_recurrence(const amt_lstm_seq* seqs_host, int n_seq, int B, int T, void* scratch, size_t scratch_bytes,
+                        amt_stream_t stream) {
+  return amt::run_lstm(seqs_host, n_seq, B, T, scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

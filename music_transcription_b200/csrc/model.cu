@@ -1,0 +1,327 @@
+// amt_model: eval-mode forward of CNNRNNModel / CNNRNNModelLarge
+// (reference models/cnn_rnn_model.py:57-74 and :262-349) as a fixed sequence of
+// kernel launches on the caller's stream.  All intermediate tensors live in the
+// caller-provided workspace; weights are the packed tensors registered by name.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace amt {
+
+struct Tensor {
+  const void* ptr = nullptr;
+  size_t nbytes = 0;
+};
+
+}  // namespace amt
+
+struct amt_model {
+  amt_model_config cfg;
+  std::map<std::string, amt::Tensor> tensors;
+  bool finalized = false;
+  // derived sizes
+  int F1, F2, F3;       // frequency bins after 1, 2, 3 pools
+  int Kfeat;            // LSTM input width
+  int H, Hl, D;         // hidden, local hidden, rnn output width
+  int Ng0;              // gate columns of layer 0 (all sequences)
+  int n_out, n_out_pad; // head columns (88 * n_heads) and padded GEMM N
+};
+
+namespace amt {
+
+struct Expect { std::string name; size_t nbytes; };
+
+static std::vector<Expect> expected_tensors(const amt_model& m) {
+  const amt_model_config& c = m.cfg;
+  std::vector<Expect> e;
+  auto bf = [](size_t n) { return n * 2; };
+  auto f32 = [](size_t n) { return n * 4; };
+  e.push_back({"conv1.w", f32(32 * 9)});
+  e.push_back({"conv1.b", f32(32)});
+  if (c.kind == AMT_MODEL_CNN_RNN) {
+    e.push_back({"c2.w", bf(64ull * 9 * 64)});
+    e.push_back({"c2.b", f32(64)});
+  } else {
+    e.push_back({"res1.c1.w", bf(64ull * 9 * 64)});
+    e.push_back({"res1.c1.b", f32(64)});
+    e.push_back({"res1.c2.w", bf(64ull * (9 * 64 + 64))});
+    e.push_back({"res1.c2.b", f32(64)});
+    e.push_back({"res2.c1.w", bf(128ull * 9 * 64)});
+    e.push_back({"res2.c1.b", f32(128)});
+    e.push_back({"res2.c2.w", bf(128ull * (9 * 128 + 64))});
+    e.push_back({"res2.c2.b", f32(128)});
+    e.push_back({"freq.w", bf(256ull * 21 * 128)});
+    e.push_back({"freq.b", f32(256)});
+  }
+  for (int l = 0; l < c.layers; ++l) {
+    const size_t N = l == 0 ? m.Ng0 : 8ull * m.H;
+    const size_t K = l == 0 ? m.Kfeat : 2ull * m.H;
+    e.push_back({"rnn" + std::to_string(l) + ".wih", bf(N * K)});
+    e.push_back({"rnn" + std::to_string(l) + ".b", f32(N)});
+    for (int d = 0; d < 2; ++d) e.push_back({"rnn" + std::to_string(l) + ".whh" + std::to_string(d), bf(4ull * m.H * m.H)});
+  }
+  if (c.kind == AMT_MODEL_CNN_RNN_LARGE) {
+    for (int d = 0; d < 2; ++d) e.push_back({"loc.whh" + std::to_string(d), bf(4ull * m.Hl * m.Hl)});
+    if (c.use_attention) {
+      e.push_back({"attn.qkv.w", bf(3ull * m.D * m.D)});
+      e.push_back({"attn.qkv.b", f32(3ull * m.D)});
+      e.push_back({"attn.proj.w", bf(1ull * m.D * m.D)});
+      e.push_back({"attn.proj.b", f32(m.D)});
+      e.push_back({"ln.w", f32(m.D)});
+      e.push_back({"ln.b", f32(m.D)});
+    }
+    if (c.use_onset_offset) {
+      e.push_back({"fc1.w", bf(1ull * m.H * m.D)});
+      e.push_back({"fc1.b", f32(m.H)});
+      e.push_back({"heads.w", bf(1ull * m.n_out_pad * m.H)});
+    } else {
+      e.push_back({"heads.w", bf(1ull * m.n_out_pad * m.D)});
+    }
+  } else {
+    e.push_back({"heads.w", bf(1ull * m.n_out_pad * m.D)});
+  }
+  e.push_back({"heads.b", f32(m.n_out_pad)});
+  return e;
+}
+
+// workspace carving --------------------------------------------------------
+struct Workspace {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Workspace(void* p) : base(static_cast<uint8_t*>(p)) {}
+  void* take(size_t bytes) {
+    void* r = base ? base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return r;
+  }
+};
+
+struct Buffers {
+  void *act1, *h1, *act2, *h2, *act3, *feat;    // CNN activations (bf16)
+  float* gx;                                     // gate pre-activations (f32), max over layers
+  void* seq_a; void* seq_b;                      // inter-layer LSTM outputs (bf16) ping-pong
+  void* rnn_bf16; float* rnn_f32;                // final LSTM features
+  void *qkv, *att; float* proj; void* normed; void* shared; float* logits;
+  void* lstm_scratch; size_t lstm_scratch_bytes;
+};
+
+static size_t carve(const amt_model& m, int B, int T, void* ws, Buffers* b) {
+  Workspace w(ws);
+  const size_t BT = static_cast<size_t>(B) * T;
+  const bool large = m.cfg.kind == AMT_MODEL_CNN_RNN_LARGE;
+  b->act1 = w.take(BT * m.F1 * 64 * 2);
+  if (large) {
+    b->h1 = w.take(BT * m.F1 * 64 * 2);
+    b->act2 = w.take(BT * m.F2 * 64 * 2);
+    b->h2 = w.take(BT * m.F2 * 128 * 2);
+    b->act3 = w.take(BT * m.F2 * 128 * 2);
+    b->feat = w.take(BT * m.F3 * 256 * 2);
+  } else {
+    b->h1 = b->act2 = b->h2 = b->act3 = nullptr;
+    b->feat = w.take(BT * m.F2 * 64 * 2);
+  }
+  const size_t gcols = std::max<size_t>(m.Ng0, 8ull * m.H);
+  b->gx = static_cast<float*>(w.take(BT * gcols * 4));
+  b->seq_a = w.take(BT * 2 * m.H * 2);
+  b->seq_b = w.take(BT * 2 * m.H * 2);
+  b->rnn_bf16 = w.take(BT * m.D * 2);
+  b->rnn_f32 = static_cast<float*>(w.take(BT * m.D * 4));
+  if (large && m.cfg.use_attention) {
+    b->qkv = w.take(BT * 3 * m.D * 2);
+    b->att = w.take(BT * m.D * 2);
+    b->proj = static_cast<float*>(w.take(BT * m.D * 4));
+    b->normed = w.take(BT * m.D * 2);
+  } else {
+    b->qkv = b->att = b->normed = nullptr;
+    b->proj = nullptr;
+  }
+  b->shared = (large && m.cfg.use_onset_offset) ? w.take(BT * m.H * 2) : nullptr;
+  b->logits = static_cast<float*>(w.take(BT * m.n_out_pad * 4));
+  // recurrence scratch: worst case is layer 0 of the large model (4 sequences)
+  amt_lstm_seq seqs[4];
+  int n = 0;
+  for (int d = 0; d < 2; ++d) { seqs[n] = amt_lstm_seq{}; seqs[n++].H = m.H; }
+  if (large) for (int d = 0; d < 2; ++d) { seqs[n] = amt_lstm_seq{}; seqs[n++].H = m.Hl; }
+  b->lstm_scratch_bytes = std::max(lstm_scratch_bytes(seqs, n, B), lstm_scratch_bytes(seqs, 2, B));
+  b->lstm_scratch = w.take(b->lstm_scratch_bytes);
+  return w.off;
+}
+
+static const void* T_(const amt_model& m, const std::string& n) { return m.tensors.at(n).ptr; }
+static const float* F_(const amt_model& m, const std::string& n) { return static_cast<const float*>(m.tensors.at(n).ptr); }
+
+static int conv(const amt_model&, const void* X, int C, const void* X2, int C2, int B, int T, int F, const void* W,
+                const float* bias, int N, int kf, int kt, void* out, int pool, cudaStream_t s) {
+  ConvGemmDesc d{};
+  d.X = X; d.C = C; d.X2 = X2; d.C2 = C2;
+  d.B = B; d.T = T; d.F = F;
+  d.W = W; d.bias = bias; d.N = N; d.kf = kf; d.kt = kt;
+  d.out = out; d.ld_out = N; d.relu = 1; d.pool = pool; d.out_f32 = 0;
+  d.boxF = 16; d.boxT = 8;
+  return run_conv_gemm(d, s);
+}
+
+static int forward(amt_model& m, const float* logmel, int B, int T, float* frame, float* onset, float* offset,
+                   void* ws, cudaStream_t s) {
+  const amt_model_config& c = m.cfg;
+  const bool large = c.kind == AMT_MODEL_CNN_RNN_LARGE;
+  Buffers b;
+  carve(m, B, T, ws, &b);
+  const int BT = B * T;
+
+  // ---- CNN ----
+  AMT_TRY(run_conv1(logmel, F_(m, "conv1.w"), F_(m, "conv1.b"), b.act1, B, c.n_mels, T, s));
+  if (large) {
+    AMT_TRY(conv(m, b.act1, 64, nullptr, 0, B, T, m.F1, T_(m, "res1.c1.w"), F_(m, "res1.c1.b"), 64, 3, 3, b.h1, 0, s));
+    AMT_TRY(conv(m, b.h1, 64, b.act1, 64, B, T, m.F1, T_(m, "res1.c2.w"), F_(m, "res1.c2.b"), 64, 3, 3, b.act2, 1, s));
+    AMT_TRY(conv(m, b.act2, 64, nullptr, 0, B, T, m.F2, T_(m, "res2.c1.w"), F_(m, "res2.c1.b"), 128, 3, 3, b.h2, 0, s));
+    AMT_TRY(conv(m, b.h2, 128, b.act2, 64, B, T, m.F2, T_(m, "res2.c2.w"), F_(m, "res2.c2.b"), 128, 3, 3, b.act3, 0, s));
+    AMT_TRY(conv(m, b.act3, 128, nullptr, 0, B, T, m.F2, T_(m, "freq.w"), F_(m, "freq.b"), 256, 7, 3, b.feat, 1, s));
+  } else {
+    AMT_TRY(conv(m, b.act1, 64, nullptr, 0, B, T, m.F1, T_(m, "c2.w"), F_(m, "c2.b"), 64, 3, 3, b.feat, 1, s));
+  }
+
+  // ---- BiLSTM stack (+ the parallel local BiLSTM of the large model on layer 0) ----
+  const void* x = b.feat;
+  int K = m.Kfeat;
+  for (int l = 0; l < c.layers; ++l) {
+    const std::string pre = "rnn" + std::to_string(l);
+    const int N = l == 0 ? m.Ng0 : 8 * m.H;
+    AMT_TRY(run_gemm(x, T_(m, pre + ".wih"), F_(m, pre + ".b"), b.gx, BT, N, K, N, 0, 1, s));
+    const bool last = l == c.layers - 1;
+    void* out_bf = last ? b.rnn_bf16 : ((l & 1) ? b.seq_b : b.seq_a);
+    const int ld_out = last ? m.D : 2 * m.H;
+    amt_lstm_seq seqs[4];
+    int n = 0;
+    for (int d = 0; d < 2; ++d) {
+      amt_lstm_seq& q = seqs[n++];
+      q.whh = T_(m, pre + ".whh" + std::to_string(d));
+      q.gx = b.gx + d * 4 * m.H;
+      q.out_bf16 = static_cast<__nv_bfloat16*>(out_bf) + d * m.H;
+      q.out_f32 = last ? b.rnn_f32 + d * m.H : nullptr;
+      q.H = m.H; q.reverse = d; q.ld_gx = N; q.ld_out = ld_out; q.ld_out32 = m.D;
+    }
+    if (large && l == 0) {
+      for (int d = 0; d < 2; ++d) {
+        amt_lstm_seq& q = seqs[n++];
+        q.whh = T_(m, "loc.whh" + std::to_string(d));
+        q.gx = b.gx + 8 * m.H + d * 4 * m.Hl;
+        q.out_bf16 = static_cast<__nv_bfloat16*>(b.rnn_bf16) + 2 * m.H + d * m.Hl;
+        q.out_f32 = b.rnn_f32 + 2 * m.H + d * m.Hl;
+        q.H = m.Hl; q.reverse = d; q.ld_gx = N; q.ld_out = m.D; q.ld_out32 = m.D;
+      }
+    }
+    AMT_TRY(run_lstm(seqs, n, B, T, b.lstm_scratch, b.lstm_scratch_bytes, s));
+    x = out_bf;
+    K = 2 * m.H;
+  }
+
+  // ---- attention + residual LayerNorm ----
+  const void* head_in = b.rnn_bf16;
+  if (large && c.use_attention) {
+    AMT_TRY(run_gemm(b.rnn_bf16, T_(m, "attn.qkv.w"), F_(m, "attn.qkv.b"), b.qkv, BT, 3 * m.D, m.D, 3 * m.D, 0, 0, s));
+    AMT_TRY(run_attention(b.qkv, b.att, B, T, c.heads, m.D / c.heads, 10.0f, s));
+    AMT_TRY(run_gemm(b.att, T_(m, "attn.proj.w"), F_(m, "attn.proj.b"), b.proj, BT, m.D, m.D, m.D, 0, 1, s));
+    AMT_TRY(run_add_layernorm(b.rnn_f32, b.proj, F_(m, "ln.w"), F_(m, "ln.b"), b.normed, BT, m.D, 1e-6f, s));
+    head_in = b.normed;
+  }
+
+  // ---- output heads ----
+  int n_heads = 1;
+  if (large && c.use_onset_offset) {
+    AMT_TRY(run_gemm(head_in, T_(m, "fc1.w"), F_(m, "fc1.b"), b.shared, BT, m.H, m.D, m.H, 1, 0, s));
+    AMT_TRY(run_gemm(b.shared, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.H, m.n_out_pad, 0, 1, s));
+    n_heads = 3;
+  } else {
+    AMT_TRY(run_gemm(head_in, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.D, m.n_out_pad, 0, 1, s));
+  }
+  AMT_TRY(run_heads_transpose(b.logits, m.n_out_pad, B, T, n_heads, frame, n_heads == 3 ? onset : nullptr,
+                              n_heads == 3 ? offset : nullptr, s));
+  return 0;
+}
+
+}  // namespace amt
+
+extern "C" {
+
+int amt_model_create(const amt_model_config* cfg, amt_model** out) {
+  using namespace amt;
+  AMT_REQUIRE(cfg && out, "model_create: NULL argument");
+  AMT_REQUIRE(cfg->kind == AMT_MODEL_CNN_RNN || cfg->kind == AMT_MODEL_CNN_RNN_LARGE, "model_create: unknown kind %d", cfg->kind);
+  AMT_REQUIRE(cfg->hidden % 128 == 0 && cfg->hidden >= 128 && cfg->hidden <= 768,
+              "model_create: hidden_size %d unsupported (multiple of 128 in 128..768)", cfg->hidden);
+  AMT_REQUIRE(cfg->layers >= 1 && cfg->layers <= 8, "model_create: num_layers %d unsupported", cfg->layers);
+  const bool large = cfg->kind == AMT_MODEL_CNN_RNN_LARGE;
+  AMT_REQUIRE(cfg->n_mels >= (large ? 8 : 4) && cfg->n_mels <= 4096, "model_create: n_mels %d unsupported", cfg->n_mels);
+  if (large && cfg->use_attention) {
+    AMT_REQUIRE(cfg->heads == 8, "model_create: the reference fixes 8 attention heads");
+    const int hd = 3 * cfg->hidden / 8;
+    AMT_REQUIRE(hd == 48 || hd == 96 || hd == 144 || hd == 192, "model_create: head_dim %d unsupported (hidden <= 512 with attention)", hd);
+  }
+  auto* m = new amt_model();
+  m->cfg = *cfg;
+  m->F1 = cfg->n_mels / 2;
+  m->F2 = m->F1 / 2;
+  m->F3 = m->F2 / 2;
+  m->H = cfg->hidden;
+  m->Hl = large ? cfg->hidden / 2 : 0;
+  m->D = large ? 2 * m->H + 2 * m->Hl : 2 * m->H;
+  m->Kfeat = large ? 256 * m->F3 : 64 * m->F2;
+  m->Ng0 = 8 * m->H + 8 * m->Hl;
+  m->n_out = (large && cfg->use_onset_offset) ? 3 * 88 : 88;
+  m->n_out_pad = (m->n_out + 127) / 128 * 128;
+  *out = m;
+  return 0;
+}
+
+int amt_model_destroy(amt_model* m) {
+  delete m;
+  return 0;
+}
+
+int amt_model_set_tensor(amt_model* m, const char* name, const void* dev_ptr, size_t nbytes) {
+  using namespace amt;
+  AMT_REQUIRE(m && name && dev_ptr, "model_set_tensor: NULL argument");
+  AMT_REQUIRE(reinterpret_cast<uintptr_t>(dev_ptr) % 16 == 0, "model_set_tensor: %s must be 16-byte aligned", name);
+  m->tensors[name] = Tensor{dev_ptr, nbytes};
+  m->finalized = false;
+  return 0;
+}
+
+int amt_model_finalize(amt_model* m) {
+  using namespace amt;
+  AMT_REQUIRE(m, "model_finalize: NULL model");
+  for (const Expect& e : expected_tensors(*m)) {
+    auto it = m->tensors.find(e.name);
+    if (it == m->tensors.end()) return set_error(AMT_ERR_STATE, "model_finalize: missing tensor '%s'", e.name.c_str());
+    if (it->second.nbytes != e.nbytes)
+      return set_error(AMT_ERR_STATE, "model_finalize: tensor '%s' has %zu bytes, expected %zu", e.name.c_str(),
+                       it->second.nbytes, e.nbytes);
+  }
+  m->finalized = true;
+  return 0;
+}
+
+size_t amt_model_workspace_bytes(const amt_model* m, int B, int T) {
+  if (!m || B <= 0 || T <= 0) return 0;
+  amt::Buffers b;
+  return amt::carve(*m, B, T, nullptr, &b);
+}
+
+int amt_model_forward(amt_model* m, const float* logmel, int B, int T, float* frame, float* onset, float* offset,
+                      void* workspace, size_t workspace_bytes, amt_stream_t stream) {
+  using namespace amt;
+  AMT_REQUIRE(m && logmel && frame && workspace, "model_forward: NULL argument");
+  AMT_REQUIRE(B >= 1 && T >= 1, "model_forward: B and T must be >= 1 (the reference's conv rejects T == 0 too)");
+  if (!m->finalized) return set_error(AMT_ERR_STATE, "model_forward: call amt_model_finalize first");
+  AMT_TRY(ensure_device());
+  AMT_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "model_forward: workspace must be 1024-byte aligned");
+  const size_t need = amt_model_workspace_bytes(m, B, T);
+  if (workspace_bytes < need) return set_error(AMT_ERR_WORKSPACE, "model_forward: workspace %zu < %zu bytes", workspace_bytes, need);
+  AMT_REQUIRE(static_cast<long long>(B) * T < (1ll << 30), "model_forward: B*T too large");
+  return forward(*m, logmel, B, T, frame, onset, offset, workspace, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+// HBM-bound kernels around the GEMMs: the Cin=1 stem convolution, residual+LayerNorm,
+// head finalisation (transpose to (B,88,T)) and sigmoid/threshold.
+#include "kernels.cuh"
+
+namespace amt {
+
+// ----------------------------------------------------------------------------
+// conv1: Conv2d(1,32,3x3,pad 1) + BatchNorm(eval, folded) + ReLU + MaxPool(2,1)
+// (reference models/cnn_rnn_model.py:30-33 and :179-182).  K = 9 is not a tensor-core
+// shape: this is a bandwidth-bound stencil.  Reads logmel [B][F][T] f32, writes
+// activations [B][T][F/2][64] bf16 (channels 32..63 are zero padding so that the next
+// layer's K blocks are whole 128-byte swizzle atoms).
+// ----------------------------------------------------------------------------
+constexpr int kC1T = 32, kC1F = 16;   // outputs per CTA: 32 frames x 16 pooled bins
+
+__global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                    int Fin, int T, int Fout) {
+  __shared__ float tile[2 * kC1F + 2][kC1T + 3];     // 34 x 35
+  __shared__ float sw[32 * 9];
+  __shared__ float sb[32];
+  const int tid = threadIdx.x;
+  const int t0 = blockIdx.x * kC1T, fo0 = blockIdx.y * kC1F, b = blockIdx.z;
+  for (int i = tid; i < 32 * 9; i += 256) sw[i] = w[i];
+  if (tid < 32) sb[tid] = bias[tid];
+  const float* xb = x + static_cast<size_t>(b) * Fin * T;
+  for (int i = tid; i < (2 * kC1F + 2) * (kC1T + 2); i += 256) {
+    const int rr = i / (kC1T + 2), cc = i - rr * (kC1T + 2);
+    const int f = 2 * fo0 - 1 + rr, t = t0 - 1 + cc;
+    tile[rr][cc] = (f >= 0 && f < Fin && t >= 0 && t < T) ? __ldg(xb + static_cast<size_t>(f) * T + t) : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int pos = tid + rep * 256;
+    const int fl = pos & (kC1F - 1), tl = pos >> 4;
+    const int fo = fo0 + fl, t = t0 + tl;
+    float in[4][3];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) in[a][c] = tile[2 * fl + a][tl + c];
+    uint32_t packed[16];
+#pragma unroll
+    for (int c2 = 0; c2 < 16; ++c2) {
+      float r[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int ch = 2 * c2 + u;
+        float a0 = sb[ch], a1 = sb[ch];
+#pragma unroll
+        for (int kf = 0; kf < 3; ++kf)
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt) {
+            const float wv = sw[ch * 9 + kf * 3 + kt];
+            a0 = fmaf(wv, in[kf][kt], a0);
+            a1 = fmaf(wv, in[kf + 1][kt], a1);
+          }
+        r[u] = fmaxf(fmaxf(a0, a1), 0.0f);
+      }
+      packed[c2] = ptx::pack_bf16(r[0], r[1]);
+    }
+    if (fo < Fout && t < T) {
+      uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * T + t) * Fout + fo) * 64);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+#pragma unroll
+      for (int j = 4; j < 8; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+int run_conv1(const float* x, const float* w, const float* bias, void* out, int B, int Fin, int T, cudaStream_t stream) {
+  const int Fout = Fin / 2;
+  AMT_REQUIRE(Fout >= 1 && T >= 1 && B >= 1 && B <= 65535, "conv1: bad sizes");
+  dim3 grid(ceil_div(T, kC1T), ceil_div(Fout, kC1F), B);
+  conv1_kernel<<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout);
+  AMT_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------
+// y = LayerNorm(a + b) * gamma + beta  (reference models/cnn_rnn_model.py:243,322; eps 1e-6)
+// one warp per row, row held in registers, two-pass variance.
+// ----------------------------------------------------------------------------
+constexpr int kLnMaxVec = 18;   // D <= 2304
+
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ out, long long rows, int D, float eps) {
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = D >> 7;                       // float4 per lane
+  const float4* pa = reinterpret_cast<const float4*>(a + row * D);
+  const float4* pb = reinterpret_cast<const float4*>(b + row * D);
+  float4 v[kLnMaxVec];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (i < nvec) {
+      const float4 x = __ldg(pa + i * 32 + lane), y = __ldg(pb + i * 32 + lane);
+      v[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float mean = sum / D;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (i < nvec) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+  const float rstd = rsqrtf(sq / D + eps);
+  uint2* po = reinterpret_cast<uint2*>(out + row * D);
+  const float4* pg = reinterpret_cast<const float4*>(gamma);
+  const float4* pbt = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (i < nvec) {
+      const float4 g = __ldg(pg + i * 32 + lane), bt = __ldg(pbt + i * 32 + lane);
+      const float y0 = (v[i].x - mean) * rstd * g.x + bt.x, y1 = (v[i].y - mean) * rstd * g.y + bt.y;
+      const float y2 = (v[i].z - mean) * rstd * g.z + bt.z, y3 = (v[i].w - mean) * rstd * g.w + bt.w;
+      po[i * 32 + lane] = make_uint2(ptx::pack_bf16(y0, y1), ptx::pack_bf16(y2, y3));
+    }
+  }
+}
+
+int run_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, void* out, long long rows,
+                      int D, float eps, cudaStream_t stream) {
+  AMT_REQUIRE(D % 128 == 0 && D <= 128 * kLnMaxVec, "layernorm: D (%d) must be a multiple of 128 and <= %d", D, 128 * kLnMaxVec);
+  add_layernorm_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(a, b, gamma, beta,
+                                                                                static_cast<__nv_bfloat16*>(out), rows, D, eps);
+  AMT_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------
+// heads: [B*T][ld] f32 (head h occupies columns h*88 .. h*88+87) -> out_h [B][88][T]
+// (the .transpose(1, 2) of reference models/cnn_rnn_model.py:74,337-345)
+// ----------------------------------------------------------------------------
+struct HeadPtrs { float* out[3]; };
+
+__global__ void __launch_bounds__(256) heads_transpose_kernel(const float* __restrict__ in, int ld, int T, int n_out,
+                                                              HeadPtrs outs) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;       // c = head*88 + pitch
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    tile[i][tx] = (t < T && c < n_out) ? __ldg(in + (static_cast<size_t>(b) * T + t) * ld + c) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    if (c < n_out && t < T) {
+      const int h = c / 88, p = c - h * 88;
+      float* o = outs.out[h];
+      if (o) o[(static_cast<size_t>(b) * 88 + p) * T + t] = tile[tx][i];
+    }
+  }
+}
+
+int run_heads_transpose(const float* in, int ld, int B, int T, int n_heads, float* o0, float* o1, float* o2,
+                        cudaStream_t stream) {
+  HeadPtrs hp{{o0, o1, o2}};
+  const int n_out = n_heads * 88;
+  dim3 grid(ceil_div(T, 32), ceil_div(n_out, 32), B);
+  heads_transpose_kernel<<<grid, 256, 0, stream>>>(in, ld, T, n_out, hp);
+  AMT_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------
+// probs = sigmoid(logits); roll = probs > thr  (reference main.py:153-156)
+// ----------------------------------------------------------------------------
+__global__ void sigmoid_threshold_kernel(const float* __restrict__ logits, long long n, float thr, float* __restrict__ probs,
+                                         float* __restrict__ roll) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float p = 1.0f / (1.0f + expf(-logits[i]));
+    if (probs) probs[i] = p;
+    if (roll) roll[i] = p > thr ? 1.0f : 0.0f;
+  }
+}
+
+}  // namespace amt
+
+extern "C" int amt_sigmoid_threshold(const float* logits, int64_t n, float thr, float* probs, float* roll,
+                                     amt_stream_t stream) {
+  using namespace amt;
+  AMT_REQUIRE(logits && n >= 0, "sigmoid_threshold: bad arguments");
+  AMT_TRY(ensure_device());
+  if (n == 0) return 0;
+  const long long blocks = std::min<long long>((n + 255) / 256, 148ll * 8);
+  sigmoid_threshold_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, n, thr, probs, roll);
+  AMT_CHECK_LAUNCH();
+  return 0;
+}

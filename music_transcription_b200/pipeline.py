@@ -1,0 +1,213 @@
+"""Host-side mirror of the reference's inference functions (main.py) on top of
+the C ABI.  Same names, argument meaning and return shapes as
+
+    audio_to_mel          main.py:103-130
+    predict_chunk         main.py:133-161
+    combine_piano_rolls   main.py:164-186
+    pianoroll_to_midi     main.py:189-226   (returns a NoteList instead of a pretty_midi object:
+                                             pretty_midi is not available offline; the note
+                                             fields and their order are identical)
+
+plus the batched entry points the B200 design adds (``Frontend.logmel``,
+``extract_notes``, ``transcribe_chunks``): the reference loops over chunks one at
+a time with a host<->device hop each (main.py:258-266); here a whole batch of
+30-s chunks goes through each kernel at once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# reference defaults (main.py:16-24)
+MODEL_TYPE = "cnn_rnn_large"
+N_MELS = 320
+HIDDEN_SIZE = 512
+NUM_LAYERS = 3
+DROPOUT = 0.2
+SR = 16000
+HOP_LENGTH = 512
+N_FFT = 2048
+CHUNK_LENGTH = 30.0
+THRESHOLD = 0.5
+
+
+class Frontend:
+    """Log-mel frontend handle (filterbank + FFT tables resident on one device)."""
+
+    _cache = {}
+
+    def __init__(self, sr=SR, n_fft=N_FFT, hop_length=HOP_LENGTH, n_mels=N_MELS, fmin=0.0, fmax=None, device=None):
+        self.sr, self.n_fft, self.hop, self.n_mels = sr, n_fft, hop_length, n_mels
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise _lib.AmtError("Frontend needs a CUDA device (no CPU fallback)")
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().amt_frontend_create(sr, n_fft, hop_length, n_mels, float(fmin),
+                                                      float(fmax if fmax is not None else sr / 2.0), C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def get(cls, sr=SR, n_mels=N_MELS, hop_length=HOP_LENGTH, device=None) -> "Frontend":
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        key = (sr, n_mels, hop_length, str(dev))
+        if key not in cls._cache:
+            cls._cache[key] = cls(sr=sr, hop_length=hop_length, n_mels=n_mels, device=dev)
+        return cls._cache[key]
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().amt_frontend_destroy(self._h)
+        except Exception:
+            pass
+
+    def num_frames(self, n_samples: int) -> int:
+        return 1 + n_samples // self.hop
+
+    def filterbank(self) -> np.ndarray:
+        fb = np.empty((self.n_mels, 1 + self.n_fft // 2), dtype=np.float32)
+        _lib.check(_lib.lib().amt_frontend_filterbank_host(self._h, fb.ctypes.data))
+        return fb
+
+    def logmel(self, wav: torch.Tensor, top_db: float = 80.0) -> torch.Tensor:
+        """wav (B, n_samples) float32 CUDA -> (B, 1, n_mels, T) float32 dB, floor at per-chunk max - top_db."""
+        _lib.require_cuda(wav, "Frontend.logmel input")
+        if wav.dim() == 1:
+            wav = wav[None]
+        wav = wav.float()
+        if wav.stride(-1) != 1:
+            wav = wav.contiguous()
+        B, n = wav.shape
+        T = self.num_frames(n)
+        out = torch.empty(B, 1, self.n_mels, T, dtype=torch.float32, device=wav.device)
+        cmax = torch.empty(B, dtype=torch.float32, device=wav.device)
+        with torch.cuda.device(wav.device):
+            _lib.check(_lib.lib().amt_logmel_f32(self._h, _lib.ptr(wav), B, n, wav.stride(0), _lib.ptr(out),
+                                                 float(top_db if top_db is not None else -1.0), _lib.ptr(cmax),
+                                                 _lib.stream_ptr(wav.device)))
+        return out
+
+
+def audio_to_mel(audio_chunk, sr=SR, n_mels=N_MELS, hop_length=HOP_LENGTH, device=None):
+    """One chunk of samples (numpy or tensor) -> mel tensor (1, 1, n_mels, T) in dB, on the GPU."""
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    wav = torch.as_tensor(np.asarray(audio_chunk, dtype=np.float32) if not torch.is_tensor(audio_chunk) else audio_chunk)
+    wav = wav.to(dev, dtype=torch.float32, non_blocking=True).reshape(1, -1)
+    return Frontend.get(sr, n_mels, hop_length, dev).logmel(wav)
+
+
+def predict_chunk(model, mel_tensor, device, threshold=THRESHOLD):
+    """Binary piano roll (88, T) numpy float32 for one mel chunk (1, 1, n_mels, T)."""
+    roll = model.predict(mel_tensor.to(device), threshold=threshold)
+    return roll[0].cpu().numpy()
+
+
+def combine_piano_rolls(piano_rolls, chunk_length=CHUNK_LENGTH, sr=SR, hop_length=HOP_LENGTH):
+    """np.concatenate along time; a single roll is returned as is (main.py:177-184)."""
+    if len(piano_rolls) == 1:
+        return piano_rolls[0]
+    return np.concatenate(piano_rolls, axis=1)
+
+
+@dataclass
+class Note:
+    velocity: int
+    pitch: int
+    start: float
+    end: float
+
+
+class NoteList:
+    """Stand-in for the pretty_midi object main.py builds: ``.instruments[0].notes`` holds
+    Note(velocity=100, pitch=21+idx, start=onset/fs, end=offset/fs) in the reference's order."""
+
+    class _Instrument:
+        def __init__(self, notes):
+            self.program, self.notes = 0, notes
+
+    def __init__(self, triples: np.ndarray, fs: float, min_midi: int = 21):
+        self.triples = np.asarray(triples, dtype=np.int32).reshape(-1, 3)
+        self.fs, self.min_midi = fs, min_midi
+        notes = [Note(100, int(min_midi + p), int(s) / fs, int(e) / fs) for p, s, e in self.triples]
+        self.instruments = [NoteList._Instrument(notes)]
+
+    def __len__(self):
+        return len(self.triples)
+
+
+def extract_notes(vals: torch.Tensor, threshold: float = 0.0, cap: int | None = None) -> np.ndarray:
+    """Note grouping on the GPU.  ``vals`` is (88, T) or (n_seg, 88, T) CUDA float32 (probabilities
+    or a {0,1} roll); segments are treated as ONE roll concatenated along time, so notes crossing a
+    chunk seam merge as in main.py:270-275.  Active iff value > float32(threshold).
+    Returns int32 (n_notes, 3): (pitch_idx, onset_frame, offset_frame), pitch-major, onset ascending."""
+    _lib.require_cuda(vals, "extract_notes input")
+    if vals.dim() == 2:
+        vals = vals[None]
+    vals = vals.float()
+    if vals.stride(-1) != 1:
+        vals = vals.contiguous()
+    n_seg, n_pitch, T = vals.shape
+    dev = vals.device
+    if cap is None:
+        cap = n_pitch * ((n_seg * T + 1) // 2)          # the most notes a roll of that size can hold
+    notes = torch.empty(max(cap, 1), 3, dtype=torch.int32, device=dev)
+    counts = torch.empty(n_pitch + 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().amt_threshold_notes(_lib.ptr(vals), n_seg, n_pitch, T, vals.stride(0), vals.stride(1),
+                                                  float(np.float32(threshold)), _lib.ptr(notes), cap, _lib.ptr(counts),
+                                                  _lib.stream_ptr(dev)))
+    total = int(counts[n_pitch].item())
+    if total > cap:
+        raise _lib.AmtError(f"extract_notes: {total} notes exceed cap {cap}")
+    return notes[:total].cpu().numpy()
+
+
+def pianoroll_to_midi(pianoroll, fs, min_midi=21) -> NoteList:
+    """(88, T) roll (numpy or tensor, values {0,1}) -> notes, grouped on the GPU (main.py:204-223)."""
+    roll = torch.as_tensor(np.ascontiguousarray(pianoroll, dtype=np.float32)) if not torch.is_tensor(pianoroll) else pianoroll
+    if not roll.is_cuda:
+        roll = roll.to(f"cuda:{torch.cuda.current_device()}")
+    return NoteList(extract_notes(roll, threshold=0.0), fs, min_midi)
+
+
+def split_audio_into_chunks(y: np.ndarray, chunk_length=CHUNK_LENGTH, sr=SR) -> List[np.ndarray]:
+    """Chunking of an already-decoded mono signal (main.py:82-97): ceil(len/chunk) chunks, last one
+    zero-padded.  (Decoding/resampling, main.py:76, is a 'next' row: SURVEY.md section 8f.)"""
+    chunk_samples = int(chunk_length * sr)
+    n = int(np.ceil(len(y) / chunk_samples))
+    out = []
+    for i in range(n):
+        c = y[i * chunk_samples:min((i + 1) * chunk_samples, len(y))]
+        if len(c) < chunk_samples:
+            c = np.pad(c, (0, chunk_samples - len(c)), mode="constant")
+        out.append(c)
+    return out
+
+
+@torch.no_grad()
+def transcribe_chunks(model, wav: torch.Tensor, threshold: float = THRESHOLD, sr=SR, n_mels=N_MELS,
+                      hop_length=HOP_LENGTH, batch: int = 64, return_probs: bool = False):
+    """Batched main.py:258-275: wav (n_chunks, n_samples) CUDA -> (notes int32 (n,3), probs or None).
+    All chunks go through log-mel -> forward -> sigmoid in batches of ``batch``; notes are grouped on the
+    concatenated roll."""
+    _lib.require_cuda(wav, "transcribe_chunks input")
+    fe = Frontend.get(sr, n_mels, hop_length, wav.device)
+    n = wav.shape[0]
+    T = fe.num_frames(wav.shape[1])
+    probs = torch.empty(n, 88, T, dtype=torch.float32, device=wav.device)
+    L = _lib.lib()
+    for i in range(0, n, batch):
+        mel = fe.logmel(wav[i:i + batch])
+        logits = model(mel)
+        with torch.cuda.device(wav.device):
+            _lib.check(L.amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), 0.0, _lib.ptr(probs[i:i + batch]), 0,
+                                               _lib.stream_ptr(wav.device)))
+    notes = extract_notes(probs, threshold=threshold)
+    return notes, (probs if return_probs else None)

@@ -1,0 +1,253 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI
+(ctypes) and compared with plain fp32 PyTorch math on the same (bf16-rounded) inputs
+or with the oracle for integer work.  Run with: pytest -m gpu"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from music_transcription_b200 import _lib, synth
+from music_transcription_b200.packing import slice_order
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _stream():
+    return _lib.stream_ptr(torch.device(DEV))
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ----------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,relu,f32", [
+    (128, 256, 64, 0, 1),
+    (200, 128, 128, 1, 0),
+    (1000, 64, 192, 0, 1),
+    (938 * 2, 512, 1024, 1, 0),
+    (300, 384, 1536, 0, 1),
+    (4100, 1536, 640, 0, 0),
+])
+def test_gemm_tcgen05_matches_fp32_matmul(M, N, K, relu, f32):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = _bf(torch.randn(M, K, generator=g)).to(DEV)
+    W = _bf(torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = torch.full((M, N), float("nan"), dtype=torch.float32 if f32 else torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().amt_gemm_bf16(_lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(out), M, N, K, N, relu, f32,
+                                        _stream()))
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias
+    if relu:
+        ref = ref.relu()
+    tol = 2e-3 if f32 else 2e-2
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < tol
+
+
+def test_gemm_rejects_bad_shapes():
+    a = torch.zeros(128, 96, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(ValueError):
+        _lib.check(_lib.lib().amt_gemm_bf16(_lib.ptr(a), _lib.ptr(a), _lib.ptr(a), _lib.ptr(a), 128, 128, 96, 128, 0, 0,
+                                            _stream()))
+
+
+# ----------------------------------------------------------------------------- conv
+def _conv_ref(x_btfc, w, bias, kf, kt, relu, pool, x2=None, w2=None):
+    # x [B,T,F,C] -> NCHW with H=F, W=T
+    x = x_btfc.float().permute(0, 3, 2, 1)
+    y = F.conv2d(x, w.float(), None, padding=(kf // 2, kt // 2))
+    if x2 is not None:
+        y = y + F.conv2d(x2.float().permute(0, 3, 2, 1), w2.float(), None)
+    y = y + bias.view(1, -1, 1, 1)
+    if relu:
+        y = y.relu()
+    if pool:
+        y = F.max_pool2d(y, (2, 1))
+    return y.permute(0, 3, 2, 1).contiguous()        # [B,T,F',Co]
+
+
+def _pack_w(w):     # [Co,Ci,kf,kt] -> [Co, kf*kt*Ci]
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+@pytest.mark.parametrize("B,T,Fq,Ci,Co,kf,kt,pool,skip", [
+    (1, 16, 16, 64, 64, 3, 3, 0, 0),
+    (2, 37, 20, 64, 128, 3, 3, 1, 0),
+    (1, 50, 9, 128, 256, 7, 3, 1, 0),
+    (2, 21, 40, 128, 128, 3, 3, 0, 64),
+    (1, 938, 80, 64, 64, 3, 3, 1, 64),
+])
+def test_conv_implicit_gemm_matches_conv2d(B, T, Fq, Ci, Co, kf, kt, pool, skip):
+    g = torch.Generator().manual_seed(B * 1000 + T + Fq + Ci + Co)
+    x = _bf(torch.randn(B, T, Fq, Ci, generator=g)).to(DEV)
+    w = _bf(torch.randn(Co, Ci, kf, kt, generator=g) / (Ci * kf * kt) ** 0.5).to(DEV)
+    bias = torch.randn(Co, generator=g).to(DEV)
+    x2 = w2 = None
+    wp = _pack_w(w)
+    if skip:
+        x2 = _bf(torch.randn(B, T, Fq, skip, generator=g)).to(DEV)
+        w2 = _bf(torch.randn(Co, skip, 1, 1, generator=g) / skip ** 0.5).to(DEV)
+        wp = torch.cat([wp, _pack_w(w2)], dim=1).contiguous()
+    Fo = Fq // 2 if pool else Fq
+    out = torch.full((B, T, Fo, Co), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().amt_conv_bf16(_lib.ptr(x), _lib.ptr(x2), _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(out), B, T, Fq,
+                                        Ci, skip, Co, kf, kt, 1, pool, _stream()))
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, w, bias, kf, kt, True, pool, x2, w2)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+# ----------------------------------------------------------------------------- LSTM recurrence
+def _lstm_ref(gx, whh, reverse):
+    """gx [B,T,4H] (gate order i,f,g,o, natural), whh [4H,H] bf16; h fed back in bf16 like the kernel."""
+    B, T, G = gx.shape
+    H = G // 4
+    h = torch.zeros(B, H, device=gx.device)
+    c = torch.zeros(B, H, device=gx.device)
+    out = torch.zeros(B, T, H, device=gx.device)
+    W = whh.float()
+    for s in range(T):
+        t = T - 1 - s if reverse else s
+        gates = gx[:, t] + h.to(torch.bfloat16).float() @ W.t()
+        i, f, g, o = gates.split(H, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out[:, t] = h
+    return out
+
+
+@pytest.mark.parametrize("B,T,Hs", [(3, 12, (128,)), (16, 40, (128, 128, 64, 64)), (20, 25, (256, 256)), (5, 30, (512, 512, 256, 256))])
+def test_lstm_recurrence_matches_stepwise_reference(B, T, Hs):
+    g = torch.Generator().manual_seed(B * 100 + T)
+    L = _lib.lib()
+    n = len(Hs)
+    ncols = sum(4 * h for h in Hs)
+    gx_nat = [torch.randn(B, T, 4 * h, generator=g).to(DEV) for h in Hs]
+    whh = [_bf(torch.randn(4 * h, h, generator=g) / h ** 0.5).to(DEV) for h in Hs]
+    gx = torch.empty(B * T, ncols, device=DEV)
+    wout = sum(Hs)
+    out_bf = torch.full((B * T, wout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    out_f32 = torch.full((B * T, wout), float("nan"), device=DEV)
+    seqs = (_lib.LstmSeq * n)()
+    keep = []
+    col = ocol = 0
+    for i, h in enumerate(Hs):
+        perm = slice_order(h).to(DEV)
+        gx[:, col:col + 4 * h] = gx_nat[i].reshape(B * T, 4 * h)[:, perm]
+        wp = whh[i][perm].contiguous()
+        keep.append(wp)
+        s = seqs[i]
+        s.whh = _lib.ptr(wp)
+        s.gx = gx.data_ptr() + col * 4
+        s.out_bf16 = out_bf.data_ptr() + ocol * 2
+        s.out_f32 = out_f32.data_ptr() + ocol * 4
+        s.H, s.reverse, s.ld_gx, s.ld_out, s.ld_out32 = h, i % 2, ncols, wout, wout
+        col += 4 * h
+        ocol += h
+    nbytes = L.amt_lstm_scratch_bytes(seqs, n, B)
+    assert nbytes > 0
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    _lib.check(L.amt_lstm_recurrence(seqs, n, B, T, _lib.ptr(scratch), nbytes, _stream()))
+    torch.cuda.synchronize()
+    ocol = 0
+    for i, h in enumerate(Hs):
+        ref = _lstm_ref(gx_nat[i], whh[i], i % 2).reshape(B * T, h)
+        got = out_f32[:, ocol:ocol + h]
+        assert torch.isfinite(got).all()
+        assert (got - ref).abs().max().item() < 5e-3, (i, h)
+        assert (out_bf[:, ocol:ocol + h].float() - got).abs().max().item() < 8e-3
+        ocol += h
+
+
+# ----------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,T,hd", [(1, 64, 48), (2, 100, 48), (1, 938, 192), (2, 77, 96), (1, 130, 144)])
+def test_attention_matches_clamped_softmax(B, T, hd):
+    heads = 8
+    D = heads * hd
+    g = torch.Generator().manual_seed(T + hd)
+    qkv = _bf(torch.randn(B * T, 3 * D, generator=g) * 1.5).to(DEV)
+    out = torch.full((B * T, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().amt_attention_bf16(_lib.ptr(qkv), _lib.ptr(out), B, T, heads, hd, 10.0, _stream()))
+    torch.cuda.synchronize()
+    x = qkv.float().reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = x[0], x[1], x[2]
+    a = torch.clamp((q @ k.transpose(-2, -1)) * hd ** -0.5, -10.0, 10.0).softmax(-1)
+    ref = (a @ v).transpose(1, 2).reshape(B * T, D)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+# ----------------------------------------------------------------------------- notes / F1 (bit-exact)
+def test_notes_kernel_is_bit_exact_with_oracle_and_reference_golden():
+    from music_transcription_b200.pipeline import extract_notes
+    from oracle import notes as onotes
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "notes_reference.npz"))
+    fs = 16000 / 512
+    for name in ("random", "sparse", "full", "empty", "edges", "seam"):
+        roll = g[name + "_roll"].astype(np.float32)
+        got = extract_notes(torch.from_numpy(roll).to(DEV), threshold=0.0)
+        assert np.array_equal(got, onotes.group_notes(roll)), name
+        assert np.array_equal(got[:, 0] + 21, g[name + "_pitch"])
+        assert np.array_equal(got[:, 1] / fs, g[name + "_start"]) and np.array_equal(got[:, 2] / fs, g[name + "_end"])
+    # seam merge through the segmented view (no concatenated copy on the device)
+    segs = torch.from_numpy(np.stack([g["seam_a"], g["seam_b"]]).astype(np.float32)).to(DEV)
+    assert np.array_equal(extract_notes(segs, 0.0), onotes.group_notes(g["seam_roll"].astype(np.float32)))
+    # probabilities with values planted exactly on float32(threshold)
+    for thr in (0.5, 0.1, 0.35000000000000003):
+        p = synth.planted_probs(88, 938, [thr], seed=3, frac=0.05)
+        got = extract_notes(torch.from_numpy(p).to(DEV), threshold=thr)
+        assert np.array_equal(got, onotes.group_notes(onotes.threshold_roll(p, thr)))
+
+
+def test_f1_counts_kernel_is_bit_exact():
+    from music_transcription_b200 import evaluate as ev
+    from oracle import f1 as of1
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "f1_reference.npz"))
+    probs, rolls, lengths = g["probs"], g["rolls"].astype(np.float32), g["lengths"]
+    thr = list(np.linspace(0.01, 0.99, 100)) + [0.35000000000000003, 0.5, 0.5]
+    got = ev.f1_counts(torch.from_numpy(probs).to(DEV), torch.from_numpy(rolls).to(DEV), lengths, thr)
+    want = of1.counts_grid(probs, rolls, lengths, thr)
+    assert got.dtype == np.int64 and np.array_equal(got, want)
+    P, Y = torch.from_numpy(probs).to(DEV), torch.from_numpy(rolls).to(DEV)
+
+    def mean_at(t):
+        return float(np.mean(ev.f1_from_counts(ev.f1_counts(P, Y, lengths, [t])[:, 0])))
+    for t, f in zip(g["at_t"], g["at_f1"]):
+        assert mean_at(float(t)) == pytest.approx(float(f), abs=1e-15)
+    best_t, best_f1 = ev.threshold_schedule_walk(mean_at)
+    assert best_t == float(g["best_t"]) and best_f1 == pytest.approx(float(g["best_f1"]), abs=1e-15)
+
+
+def test_f1_counts_config5_shape_properties():
+    """50 pieces x 100 thresholds (BASELINE config 5 on one GPU): checksum identities."""
+    from music_transcription_b200 import evaluate as ev
+    n, T = 50, 938
+    lens = np.array([937, 938, 469][0:1] * n, dtype=np.int32)
+    lens[1::3], lens[2::3] = 938, 469
+    thr = np.linspace(0.01, 0.99, 100)
+    P = torch.stack([torch.from_numpy(synth.planted_probs(88, T, thr, seed=i)) for i in range(n)]).to(DEV)
+    Y = torch.stack([torch.from_numpy(synth.bernoulli_roll(88, T, 0.05, seed=i)) for i in range(n)]).to(DEV)
+    c = ev.f1_counts(P, Y, lens, thr)
+    assert c.shape == (n, 100, 3)
+    pos = np.array([int(Y[i, :, :lens[i]].sum().item()) for i in range(n)])
+    assert np.array_equal(c[:, :, 0] + c[:, :, 2], np.repeat(pos[:, None], 100, 1))     # TP + FN = positives
+    assert np.all(np.diff(c[:, :, 0] + c[:, :, 1], axis=1) <= 0)                           # predictions shrink with t
+    from oracle import f1 as of1
+    for i in (0, 7, 49):
+        assert np.array_equal(c[i], of1.counts_grid([P[i].cpu().numpy()], [Y[i].cpu().numpy()], [lens[i]], thr)[0])
+
+
+def test_sigmoid_threshold_strict_compare():
+    x = torch.tensor([0.0, -2.1972246, 5.0, -5.0], device=DEV)
+    probs, roll = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(_lib.lib().amt_sigmoid_threshold(_lib.ptr(x), 4, 0.5, _lib.ptr(probs), _lib.ptr(roll), _stream()))
+    assert roll.tolist() == [0.0, 0.0, 1.0, 0.0]          # sigmoid(0) == 0.5 is NOT > 0.5
+    assert torch.allclose(probs, torch.sigmoid(x), atol=1e-7)

@@ -1,0 +1,165 @@
+"""GPU parity of the drop-in boundary: log-mel frontend vs the oracle restatement,
+TranscriptionModel (CUDA kernels through the C ABI) vs the oracle fp32 forward and vs the
+golden outputs of the real reference, and the batched audio->notes pipeline.
+
+Stated tolerances (bf16 tensor-core operands, fp32 accumulation; SURVEY.md 7.2-2 measured a
+5.2e-3 probability floor for bf16-rounded weights alone):
+    log-mel  : max-abs <= 2e-2 dB, mean-abs <= 5e-4 dB vs the fp64-FFT oracle (fp32 FFT on the GPU)
+    logits   : max-abs <= 0.2, probabilities max-abs <= 4e-2, mean-abs <= 4e-3 on the stress
+               checkpoints of synth.synth_state_dict (unit-gain weights, perturbed BatchNorm: logits
+               reach +-3); a CPU emulation of the same bf16 roundings (tests/emulate.py) shows this is
+               the bf16 operand floor (0.13 / 2.4e-2 / 2.5e-3), not kernel error -- the kernels
+               themselves must agree with that emulation to 5e-2 / 1e-2 / 1e-3
+    notes / TP-FP-FN counts: bit-exact given the same probability roll (test_gpu_kernels.py)
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from music_transcription_b200 import pipeline, synth
+from music_transcription_b200.transcription_model import TranscriptionModel
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+LOGMEL_MAX_DB, LOGMEL_MEAN_DB = 2e-2, 5e-4
+LOGIT_MAX, PROB_MAX, PROB_MEAN = 0.2, 4e-2, 4e-3
+
+
+def test_frontend_filterbank_matches_oracle():
+    from oracle import frontend as ofe
+    fe = pipeline.Frontend.get(device=DEV)
+    fb = fe.filterbank()
+    ref = ofe.mel_filterbank()
+    assert fb.shape == ref.shape and np.abs(fb - ref).max() < 1e-7
+    assert np.array_equal(fb > 0, ref > 0)
+
+
+@pytest.mark.parametrize("case", ["chord0", "chord5", "silence", "noise", "short", "impulse"])
+def test_logmel_matches_oracle(case):
+    from oracle import frontend as ofe
+    n = 480000
+    if case.startswith("chord"):
+        y = synth.piano_chord(int(case[5:]), n_samples=96000)
+    elif case == "silence":
+        y = np.zeros(32000, np.float32)
+    elif case == "noise":
+        y = np.random.default_rng(1).uniform(-1, 1, 48000).astype(np.float32)
+    elif case == "short":
+        y = synth.piano_chord(2, n_samples=3000)
+    else:
+        y = np.zeros(20000, np.float32)
+        y[7777] = 1.0
+    mel = pipeline.audio_to_mel(y, device=DEV)
+    ref = ofe.logmel(y)
+    assert mel.shape == (1, 1, 320, 1 + len(y) // 512) and mel.dtype == torch.float32
+    d = np.abs(mel[0, 0].cpu().numpy() - ref)
+    assert d.max() < LOGMEL_MAX_DB and d.mean() < LOGMEL_MEAN_DB, (case, d.max(), d.mean())
+
+
+def test_logmel_full_chunk_batch_shapes_and_floor():
+    from oracle import frontend as ofe
+    wav = torch.from_numpy(synth.piano_chord_batch([0, 1, 2])).to(DEV)
+    fe = pipeline.Frontend.get(device=DEV)
+    mel = fe.logmel(wav)
+    assert mel.shape == (3, 1, 320, 938)
+    for i in range(3):
+        m = mel[i, 0]
+        assert float(m.min()) >= float(m.max()) - 80.0 - 1e-4         # per-chunk top_db floor (main.py:125)
+    ref = ofe.logmel(synth.piano_chord(1))
+    d = np.abs(mel[1, 0].cpu().numpy() - ref)
+    assert d.max() < LOGMEL_MAX_DB and d.mean() < LOGMEL_MEAN_DB, (d.max(), d.mean())
+
+
+def _load_case(path):
+    g = np.load(path)
+    n_mels, H, L, B, T, attn, heads, seed, xseed = [int(v) for v in g["cfg"]]
+    mt = str(g["model_type"])
+    sd = synth.synth_state_dict(mt, n_mels, H, L, seed=seed, use_attention=bool(attn), use_onset_offset_heads=bool(heads))
+    return g, mt, n_mels, H, L, bool(attn), bool(heads), sd
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "model_*_*.npz"))),
+                         ids=lambda p: os.path.basename(p)[6:-4])
+def test_model_matches_reference_golden(path):
+    g, mt, n_mels, H, L, attn, heads, sd = _load_case(path)
+    m = TranscriptionModel(model_type=mt, n_mels=n_mels, hidden_size=H, num_layers=L, dropout=0.2, device=DEV,
+                           use_attention=attn, use_onset_offset_heads=heads)
+    m.load_state_dict(sd, strict=True)          # reference .pth key set
+    m.eval()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    out = m(x)
+    assert out.shape == g["frame"].shape and out.dtype == torch.float32 and out.device.type == "cuda"
+    got = {"frame": out}
+    if mt.endswith("large") and heads:
+        allh = m(x, return_all_heads=True)
+        assert sorted(allh) == ["frame", "offset", "onset"]
+        assert torch.equal(allh["frame"], out)
+        got = allh
+    for k, v in got.items():
+        ref = torch.from_numpy(g[k])
+        dl = (v.cpu() - ref).abs()
+        dp = (torch.sigmoid(v.cpu()) - torch.sigmoid(ref)).abs()
+        assert dl.max() < LOGIT_MAX and dp.max() < PROB_MAX and dp.mean() < PROB_MEAN, (k, dl.max(), dp.max(), dp.mean())
+    # kernels vs a CPU emulation of the same bf16 roundings: isolates kernel error from the bf16 floor
+    from music_transcription_b200.packing import pack_state_dict
+    from tests.emulate import emu_forward
+    emu = emu_forward(pack_state_dict(sd, mt, n_mels, H, L, attn, heads), torch.from_numpy(g["x"]), mt, n_mels, H, L,
+                      attn, heads, bf16_acts=True)
+    for k, v in got.items():
+        dl = (v.cpu() - emu[k]).abs()
+        dp = (torch.sigmoid(v.cpu()) - torch.sigmoid(emu[k])).abs()
+        assert dl.max() < 5e-2 and dp.max() < 1e-2 and dp.mean() < 1e-3, ("emu", k, dl.max(), dp.max(), dp.mean())
+    pred = m.predict(x, threshold=0.5)
+    assert pred.shape == g["pred"].shape and set(np.unique(pred.cpu().numpy())) <= {0.0, 1.0}
+    assert (pred.cpu().numpy() != g["pred"]).mean() < 0.02
+
+
+def test_model_rejects_bad_inputs():
+    with pytest.raises(ValueError):
+        TranscriptionModel(model_type="nope", device=DEV)
+    m = TranscriptionModel(model_type="cnn_rnn", n_mels=64, hidden_size=128, num_layers=1, device=DEV)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 64, 0, device=DEV))
+    with pytest.raises(Exception):
+        m(torch.zeros(1, 1, 64, 10))          # CPU tensor: no fallback
+
+
+def test_canonical_large_model_vs_oracle_full_chunk():
+    """CNNRNNModelLarge at the reference's canonical config (n_mels 320, hidden 512, 3 layers), one
+    30-s chunk of real log-mel; oracle = fp32 PyTorch restatement on the CPU."""
+    from oracle import model as omodel
+    sd = synth.synth_state_dict("cnn_rnn_large", 320, 512, 3, seed=1)
+    m = TranscriptionModel("cnn_rnn_large", n_mels=320, hidden_size=512, num_layers=3, dropout=0.2, device=DEV)
+    m.load_state_dict(sd)
+    wav = torch.from_numpy(synth.piano_chord_batch([0, 3])).to(DEV)
+    mel = pipeline.Frontend.get(device=DEV).logmel(wav)
+    out = m(mel, return_all_heads=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = omodel.large_forward(sd, mel.cpu(), 512, 3, return_all_heads=True)
+    for k in ("frame", "onset", "offset"):
+        dl = (out[k].cpu() - ref[k]).abs()
+        dp = (torch.sigmoid(out[k].cpu()) - torch.sigmoid(ref[k])).abs()
+        assert dl.max() < LOGIT_MAX and dp.max() < PROB_MAX and dp.mean() < PROB_MEAN, (k, dl.max(), dp.max(), dp.mean())
+    # batch independence: chunk 1 alone gives the same logits as inside the batch
+    solo = m(mel[1:2])
+    assert (solo[0] - out["frame"][1]).abs().max() < 1e-5
+
+
+def test_transcribe_chunks_end_to_end_notes_match_oracle_on_same_probs():
+    from oracle import notes as onotes
+    sd = synth.synth_state_dict("cnn_rnn", 320, 128, 1, seed=2, gain=2.0)
+    m = TranscriptionModel("cnn_rnn", n_mels=320, hidden_size=128, num_layers=1, device=DEV)
+    m.load_state_dict(sd)
+    wav = torch.from_numpy(synth.piano_chord_batch([0, 1, 2], n_samples=160000)).to(DEV)
+    notes, probs = pipeline.transcribe_chunks(m, wav, threshold=0.5, batch=2, return_probs=True)
+    p = probs.cpu().numpy()
+    rolls = [onotes.threshold_roll(p[i], 0.5) for i in range(3)]
+    want = onotes.group_notes(onotes.combine_piano_rolls(rolls))
+    assert np.array_equal(notes, want)
+    nl = pipeline.pianoroll_to_midi(onotes.combine_piano_rolls(rolls), fs=16000 / 512)
+    assert len(nl) == len(want) and all(n.velocity == 100 for n in nl.instruments[0].notes)
