@@ -45,6 +45,8 @@ const char* amt_version(void);
 const char* amt_last_error(void);
 /* 0 when the current device can run the kernels (compute capability 10.x). */
 int amt_device_check(void);
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+uint64_t amt_launch_count(void);
 
 /* ---- log-mel frontend --------------------------------------------------- */
 /* Replaces librosa.feature.melspectrogram + librosa.power_to_db as called at
@@ -96,6 +98,12 @@ size_t amt_model_workspace_bytes(const amt_model* m, int B, int T);
  * amt_model_workspace_bytes(m,B,T) bytes, 1024-byte aligned. */
 int amt_model_forward(amt_model* m, const float* logmel, int B, int T, float* frame, float* onset,
                       float* offset, void* workspace, size_t workspace_bytes, amt_stream_t stream);
+
+/* Per-stage device timing of amt_model_forward (CUDA events on the caller's stream around every
+ * kernel launch).  enable != 0 starts/resets accumulation; read synchronises the pending events
+ * and returns the number of stages, filling names (cap x 32 chars), total ms and launch counts. */
+int amt_model_profile_enable(amt_model* m, int enable);
+int amt_model_profile_read(amt_model* m, char* names, float* total_ms, int* launches, int cap);
 
 /* ---- sigmoid / threshold / notes ---------------------------------------- */
 /* probs = sigmoid(logits); roll = (probs > thr) as float {0,1}

@@ -3,6 +3,8 @@
 
 namespace amt {
 
+unsigned long long launch_count();
+
 char* last_error_buf() {
   static thread_local char buf[512] = {0};
   return buf;
@@ -15,6 +17,10 @@ int set_error(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 static int g_sms = 0;
 static int g_cc_major = -1;
@@ -96,5 +102,6 @@ extern "C" {
 const char* amt_version(void) { return "amt-sm100 0.1.0"; }
 const char* amt_last_error(void) { return amt::last_error_buf(); }
 int amt_device_check(void) { return amt::ensure_device(); }
+uint64_t amt_launch_count(void) { return amt::launch_count(); }
 
 }  // extern "C"

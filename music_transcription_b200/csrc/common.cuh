@@ -30,6 +30,7 @@ int set_error(int code, const char* fmt, ...);
 
 #define AMT_CHECK_LAUNCH()                                                                 \
   do {                                                                                     \
+    amt::count_launch();                                                                   \
     cudaError_t _e = cudaGetLastError();                                                   \
     if (_e != cudaSuccess)                                                                 \
       return amt::set_error(AMT_ERR_CUDA, "kernel launch failed: %s (%s:%d)",              \
@@ -50,6 +51,7 @@ int set_error(int code, const char* fmt, ...);
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
+void count_launch();                  // every kernel launch of the library bumps amt_launch_count()
 int num_sms();                        // cached SM count of the current device
 int ensure_device();                  // AMT_ERR_DEVICE unless cc 10.x
 

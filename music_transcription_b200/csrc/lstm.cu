@@ -254,6 +254,7 @@ static int lstm_launch(const LstmParams& p, int grid, size_t smem, cudaStream_t 
   void* args[] = {const_cast<LstmParams*>(&p)};
   AMT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_recurrence_kernel<BC>), dim3(grid), dim3(128), args,
                                        smem, stream));
+  count_launch();
   return 0;
 }
 

@@ -17,7 +17,53 @@ struct Tensor {
 
 }  // namespace amt
 
+namespace amt {
+
+// CUDA-event stage timer: one (start, stop) pair per stage per forward call; pending pairs are
+// folded into the totals at the next forward call or at read time.
+struct Profiler {
+  struct Stage { std::string name; double ms = 0; int launches = 0; };
+  struct Pending { int stage; cudaEvent_t a, b; };
+  bool enabled = false;
+  std::vector<Stage> stages;
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  int stage_id(const std::string& n) {
+    for (size_t i = 0; i < stages.size(); ++i) if (stages[i].name == n) return (int)i;
+    stages.push_back(Stage{n});
+    return (int)stages.size() - 1;
+  }
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void begin(const std::string& n, cudaStream_t s) {
+    if (!enabled) return;
+    Pending p{stage_id(n), get(), get()};
+    cudaEventRecord(p.a, s);
+    pending.push_back(p);
+  }
+  void end(cudaStream_t s) {
+    if (!enabled || pending.empty()) return;
+    cudaEventRecord(pending.back().b, s);
+  }
+  void fold() {
+    for (Pending& p : pending) {
+      cudaEventSynchronize(p.b);
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { stages[p.stage].ms += ms; stages[p.stage].launches += 1; }
+      pool.push_back(p.a); pool.push_back(p.b);
+    }
+    pending.clear();
+  }
+  void reset() { fold(); stages.clear(); }
+  ~Profiler() { for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); } for (auto e : pool) cudaEventDestroy(e); }
+};
+
+}  // namespace amt
+
 struct amt_model {
+  amt::Profiler prof;
   amt_model_config cfg;
   std::map<std::string, amt::Tensor> tensors;
   bool finalized = false;
@@ -170,17 +216,25 @@ static int forward(amt_model& m, const float* logmel, int B, int T, float* frame
   Buffers b;
   carve(m, B, T, ws, &b);
   const int BT = B * T;
+  if (m.prof.enabled) m.prof.fold();      // previous call's events (host sync; profiling mode only)
+#define STAGE(name, call)               \
+  do {                                  \
+    m.prof.begin(name, s);              \
+    const int _st = (call);             \
+    m.prof.end(s);                      \
+    if (_st != 0) return _st;           \
+  } while (0)
 
   // ---- CNN ----
-  AMT_TRY(run_conv1(logmel, F_(m, "conv1.w"), F_(m, "conv1.b"), b.act1, B, c.n_mels, T, s));
+  STAGE("conv1", run_conv1(logmel, F_(m, "conv1.w"), F_(m, "conv1.b"), b.act1, B, c.n_mels, T, s));
   if (large) {
-    AMT_TRY(conv(m, b.act1, 64, nullptr, 0, B, T, m.F1, T_(m, "res1.c1.w"), F_(m, "res1.c1.b"), 64, 3, 3, b.h1, 0, s));
-    AMT_TRY(conv(m, b.h1, 64, b.act1, 64, B, T, m.F1, T_(m, "res1.c2.w"), F_(m, "res1.c2.b"), 64, 3, 3, b.act2, 1, s));
-    AMT_TRY(conv(m, b.act2, 64, nullptr, 0, B, T, m.F2, T_(m, "res2.c1.w"), F_(m, "res2.c1.b"), 128, 3, 3, b.h2, 0, s));
-    AMT_TRY(conv(m, b.h2, 128, b.act2, 64, B, T, m.F2, T_(m, "res2.c2.w"), F_(m, "res2.c2.b"), 128, 3, 3, b.act3, 0, s));
-    AMT_TRY(conv(m, b.act3, 128, nullptr, 0, B, T, m.F2, T_(m, "freq.w"), F_(m, "freq.b"), 256, 7, 3, b.feat, 1, s));
+    STAGE("res1.c1", conv(m, b.act1, 64, nullptr, 0, B, T, m.F1, T_(m, "res1.c1.w"), F_(m, "res1.c1.b"), 64, 3, 3, b.h1, 0, s));
+    STAGE("res1.c2", conv(m, b.h1, 64, b.act1, 64, B, T, m.F1, T_(m, "res1.c2.w"), F_(m, "res1.c2.b"), 64, 3, 3, b.act2, 1, s));
+    STAGE("res2.c1", conv(m, b.act2, 64, nullptr, 0, B, T, m.F2, T_(m, "res2.c1.w"), F_(m, "res2.c1.b"), 128, 3, 3, b.h2, 0, s));
+    STAGE("res2.c2", conv(m, b.h2, 128, b.act2, 64, B, T, m.F2, T_(m, "res2.c2.w"), F_(m, "res2.c2.b"), 128, 3, 3, b.act3, 0, s));
+    STAGE("freq", conv(m, b.act3, 128, nullptr, 0, B, T, m.F2, T_(m, "freq.w"), F_(m, "freq.b"), 256, 7, 3, b.feat, 1, s));
   } else {
-    AMT_TRY(conv(m, b.act1, 64, nullptr, 0, B, T, m.F1, T_(m, "c2.w"), F_(m, "c2.b"), 64, 3, 3, b.feat, 1, s));
+    STAGE("c2", conv(m, b.act1, 64, nullptr, 0, B, T, m.F1, T_(m, "c2.w"), F_(m, "c2.b"), 64, 3, 3, b.feat, 1, s));
   }
 
   // ---- BiLSTM stack (+ the parallel local BiLSTM of the large model on layer 0) ----
@@ -189,7 +243,7 @@ static int forward(amt_model& m, const float* logmel, int B, int T, float* frame
   for (int l = 0; l < c.layers; ++l) {
     const std::string pre = "rnn" + std::to_string(l);
     const int N = l == 0 ? m.Ng0 : 8 * m.H;
-    AMT_TRY(run_gemm(x, T_(m, pre + ".wih"), F_(m, pre + ".b"), b.gx, BT, N, K, N, 0, 1, s));
+    STAGE(pre + ".gemm", run_gemm(x, T_(m, pre + ".wih"), F_(m, pre + ".b"), b.gx, BT, N, K, N, 0, 1, s));
     const bool last = l == c.layers - 1;
     void* out_bf = last ? b.rnn_bf16 : ((l & 1) ? b.seq_b : b.seq_a);
     const int ld_out = last ? m.D : 2 * m.H;
@@ -213,7 +267,7 @@ static int forward(amt_model& m, const float* logmel, int B, int T, float* frame
         q.H = m.Hl; q.reverse = d; q.ld_gx = N; q.ld_out = m.D; q.ld_out32 = m.D;
       }
     }
-    AMT_TRY(run_lstm(seqs, n, B, T, b.lstm_scratch, b.lstm_scratch_bytes, s));
+    STAGE(pre + ".rec", run_lstm(seqs, n, B, T, b.lstm_scratch, b.lstm_scratch_bytes, s));
     x = out_bf;
     K = 2 * m.H;
   }
@@ -221,24 +275,25 @@ static int forward(amt_model& m, const float* logmel, int B, int T, float* frame
   // ---- attention + residual LayerNorm ----
   const void* head_in = b.rnn_bf16;
   if (large && c.use_attention) {
-    AMT_TRY(run_gemm(b.rnn_bf16, T_(m, "attn.qkv.w"), F_(m, "attn.qkv.b"), b.qkv, BT, 3 * m.D, m.D, 3 * m.D, 0, 0, s));
-    AMT_TRY(run_attention(b.qkv, b.att, B, T, c.heads, m.D / c.heads, 10.0f, s));
-    AMT_TRY(run_gemm(b.att, T_(m, "attn.proj.w"), F_(m, "attn.proj.b"), b.proj, BT, m.D, m.D, m.D, 0, 1, s));
-    AMT_TRY(run_add_layernorm(b.rnn_f32, b.proj, F_(m, "ln.w"), F_(m, "ln.b"), b.normed, BT, m.D, 1e-6f, s));
+    STAGE("attn.qkv", run_gemm(b.rnn_bf16, T_(m, "attn.qkv.w"), F_(m, "attn.qkv.b"), b.qkv, BT, 3 * m.D, m.D, 3 * m.D, 0, 0, s));
+    STAGE("attn.core", run_attention(b.qkv, b.att, B, T, c.heads, m.D / c.heads, 10.0f, s));
+    STAGE("attn.proj", run_gemm(b.att, T_(m, "attn.proj.w"), F_(m, "attn.proj.b"), b.proj, BT, m.D, m.D, m.D, 0, 1, s));
+    STAGE("add_ln", run_add_layernorm(b.rnn_f32, b.proj, F_(m, "ln.w"), F_(m, "ln.b"), b.normed, BT, m.D, 1e-6f, s));
     head_in = b.normed;
   }
 
   // ---- output heads ----
   int n_heads = 1;
   if (large && c.use_onset_offset) {
-    AMT_TRY(run_gemm(head_in, T_(m, "fc1.w"), F_(m, "fc1.b"), b.shared, BT, m.H, m.D, m.H, 1, 0, s));
-    AMT_TRY(run_gemm(b.shared, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.H, m.n_out_pad, 0, 1, s));
+    STAGE("fc1", run_gemm(head_in, T_(m, "fc1.w"), F_(m, "fc1.b"), b.shared, BT, m.H, m.D, m.H, 1, 0, s));
+    STAGE("heads", run_gemm(b.shared, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.H, m.n_out_pad, 0, 1, s));
     n_heads = 3;
   } else {
-    AMT_TRY(run_gemm(head_in, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.D, m.n_out_pad, 0, 1, s));
+    STAGE("heads", run_gemm(head_in, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.D, m.n_out_pad, 0, 1, s));
   }
-  AMT_TRY(run_heads_transpose(b.logits, m.n_out_pad, B, T, n_heads, frame, n_heads == 3 ? onset : nullptr,
-                              n_heads == 3 ? offset : nullptr, s));
+  STAGE("heads.transpose", run_heads_transpose(b.logits, m.n_out_pad, B, T, n_heads, frame, n_heads == 3 ? onset : nullptr,
+                                               n_heads == 3 ? offset : nullptr, s));
+#undef STAGE
   return 0;
 }
 
@@ -302,6 +357,27 @@ int amt_model_finalize(amt_model* m) {
   }
   m->finalized = true;
   return 0;
+}
+
+int amt_model_profile_enable(amt_model* m, int enable) {
+  using namespace amt;
+  AMT_REQUIRE(m, "model_profile_enable: NULL model");
+  m->prof.reset();
+  m->prof.enabled = enable != 0;
+  return 0;
+}
+
+int amt_model_profile_read(amt_model* m, char* names, float* total_ms, int* launches, int cap) {
+  using namespace amt;
+  AMT_REQUIRE(m && names && total_ms && launches && cap >= 0, "model_profile_read: bad arguments");
+  m->prof.fold();
+  const int n = static_cast<int>(m->prof.stages.size());
+  for (int i = 0; i < n && i < cap; ++i) {
+    snprintf(names + 32 * i, 32, "%s", m->prof.stages[i].name.c_str());
+    total_ms[i] = static_cast<float>(m->prof.stages[i].ms);
+    launches[i] = m->prof.stages[i].launches;
+  }
+  return n;
 }
 
 size_t amt_model_workspace_bytes(const amt_model* m, int B, int T) {

@@ -169,6 +169,18 @@ def extract_notes(vals: torch.Tensor, threshold: float = 0.0, cap: int | None = 
     return notes[:total].cpu().numpy()
 
 
+def extract_notes_async(vals: torch.Tensor, threshold: float, notes_out: torch.Tensor, counts_out: torch.Tensor) -> None:
+    """Launch-only variant of ``extract_notes`` (no host sync): writes int32 triples into ``notes_out``
+    (cap = notes_out.shape[0]) and per-pitch counts + total into ``counts_out`` (n_pitch + 1)."""
+    if vals.dim() == 2:
+        vals = vals[None]
+    n_seg, n_pitch, T = vals.shape
+    with torch.cuda.device(vals.device):
+        _lib.check(_lib.lib().amt_threshold_notes(_lib.ptr(vals), n_seg, n_pitch, T, vals.stride(0), vals.stride(1),
+                                                  float(np.float32(threshold)), _lib.ptr(notes_out), notes_out.shape[0],
+                                                  _lib.ptr(counts_out), _lib.stream_ptr(vals.device)))
+
+
 def pianoroll_to_midi(pianoroll, fs, min_midi=21) -> NoteList:
     """(88, T) roll (numpy or tensor, values {0,1}) -> notes, grouped on the GPU (main.py:204-223)."""
     roll = torch.as_tensor(np.ascontiguousarray(pianoroll, dtype=np.float32)) if not torch.is_tensor(pianoroll) else pianoroll

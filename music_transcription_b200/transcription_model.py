@@ -205,5 +205,23 @@ class TranscriptionModel(nn.Module):
                                                          _lib.ptr(roll), _lib.stream_ptr(logits.device)))
         return roll
 
+    # ------------------------------------------------------------------ profiling (bench.py)
+    def profile(self, enable: bool = True) -> None:
+        """Start (or stop) per-stage CUDA-event timing inside amt_model_forward."""
+        if self._handle is None:
+            raise _lib.AmtError("profile(): run one forward first so the weights are packed")
+        _lib.check(_lib.lib().amt_model_profile_enable(self._handle, int(enable)))
+
+    def profile_read(self):
+        """[(stage, total_ms, launches)] accumulated since profile(True)."""
+        cap = 64
+        names = C.create_string_buffer(32 * cap)
+        ms = (C.c_float * cap)()
+        launches = (C.c_int * cap)()
+        n = _lib.lib().amt_model_profile_read(self._handle, names, ms, launches, cap)
+        if n < 0:
+            _lib.check(n)
+        return [(names.raw[32 * i:32 * (i + 1)].split(b"\0")[0].decode(), float(ms[i]), int(launches[i])) for i in range(min(n, cap))]
+
     def compute_loss(self, logits, targets, lengths=None):
         raise NotImplementedError("training losses are outside the B200 inference hot path (SURVEY.md section 8f, rank 4)")
