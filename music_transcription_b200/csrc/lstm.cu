@@ -129,11 +129,27 @@ __global__ void __launch_bounds__(128, 1) lstm_recurrence_kernel(const LstmParam
       // gather h_{t-1} (BC x H bf16) from L2 into the swizzled B-operand tile
       const uint4* hsrc = reinterpret_cast<const uint4*>(hbuf + static_cast<size_t>((step - 1) & 1) * BC * p.Hmax);
       const int chunks_per_row = H >> 3;
-      for (int e = tid; e < BC * chunks_per_row; e += 128) {
-        const int row = e / chunks_per_row;
-        const int cc = e - row * chunks_per_row;
-        const uint4 v = ptx::ld_cg_v4(hsrc + static_cast<size_t>(row) * (p.Hmax >> 3) + cc);
-        *reinterpret_cast<uint4*>(h_smem + (cc >> 3) * (BC * 128) + ptx::sw128_offset(row, cc & 7)) = v;
+      const int total = BC * chunks_per_row;
+      // 8 independent 16-byte L2 loads in flight per thread before the first dependent smem store
+      for (int e0 = tid; e0 < total; e0 += 128 * 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * 128;
+          if (e < total) {
+            const int row = e / chunks_per_row;
+            v[u] = ptx::ld_cg_v4(hsrc + static_cast<size_t>(row) * (p.Hmax >> 3) + (e - row * chunks_per_row));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * 128;
+          if (e < total) {
+            const int row = e / chunks_per_row;
+            const int cc = e - row * chunks_per_row;
+            *reinterpret_cast<uint4*>(h_smem + (cc >> 3) * (BC * 128) + ptx::sw128_offset(row, cc & 7)) = v[u];
+          }
+        }
       }
       ptx::fence_proxy_async_smem();
       __syncthreads();
@@ -192,8 +208,9 @@ __global__ void __launch_bounds__(128, 1) lstm_recurrence_kernel(const LstmParam
     }
 
     // publish h_t to the sibling slices
+    // bar.sync orders every thread's h stores before thread 0's gpu-scope release (cumulativity),
+    // so no per-thread __threadfence() is needed on this latency-critical path.
     ptx::tc_fence_before();
-    __threadfence();
     __syncthreads();
     if (tid == 0) ptx::red_release_gpu_add(flag, 1u);
   }
