@@ -185,6 +185,26 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 4) tmem_ld_32x32b_x4(taddr, r);
+  else if constexpr (N == 8) tmem_ld_32x32b_x8(taddr, r);
+  else if constexpr (N == 16) tmem_ld_32x32b_x16(taddr, r);
+  else tmem_ld_32x32b_x32(taddr, r);
+}
+
 // K-major, 128-byte-swizzled shared-memory operand descriptor (rows of 64 bf16 =
 // 128 B; 8-row groups 1024 B apart).  `smem_addr` must be the 1024-B-aligned tile
 // base plus k_byte_offset (< 128) for the K slice inside the swizzle atom.

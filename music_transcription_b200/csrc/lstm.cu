@@ -7,14 +7,19 @@
 // for several independent sequences at once (forward / reverse directions, the main
 // and the local LSTM, and groups of BC chunks).
 //
-// Decomposition: one CTA per (batch group, sequence, slice of 32 hidden units).  The
-// CTA keeps its 128 x H slice of W_hh (4 gates x 32 units, bf16) resident in shared
-// memory for all T steps as the K-major swizzled A operand of tcgen05.mma; per step
-// it gathers h_{t-1} (BC x H bf16, published by the sibling slices through L2) as the
-// B operand, issues H/16 MMAs into a 128 x BC fp32 TMEM accumulator, and finishes the
-// cell update in registers (cell state never leaves the SM, fp32).  Slices of one
-// sequence synchronise per step through a release/acquire counter in global memory;
-// the launch is cooperative so all CTAs are co-resident.
+// Decomposition: one CTA (512 threads) per (batch group, sequence, slice of 32 hidden
+// units).  The CTA keeps its 128 x H slice of W_hh (4 gates x 32 units, bf16) resident in
+// shared memory for all T steps as the K-major swizzled A operand of tcgen05.mma; per
+// step it gathers h_{t-1} (BC x H bf16, published by the sibling slices through L2) as
+// the B operand, one thread issues H/16 MMAs into a 128 x BC fp32 TMEM accumulator, and
+// 16 warps finish the cell update: warp w reads TMEM lane quarter w%4, column group w/4
+// (the 4 gates of a unit sit in 4 adjacent lanes of ONE warp, so the gate exchange is a
+// warp-private smem transpose), each thread then owns BC/16 cells whose fp32 cell state
+// never leaves its registers.  Slices of one sequence synchronise per step through a
+// release/acquire counter in global memory; the launch is cooperative so all CTAs are
+// co-resident.  The step is latency-bound, so everything is arranged to shorten the
+// dependent chain: gx prefetched before the wait, all h loads in flight at once, no
+// per-thread fences, 4 warps per scheduler for the transcendental-heavy epilogue.
 #include <cooperative_groups.h>
 
 #include "kernels.cuh"
@@ -22,6 +27,7 @@
 namespace amt {
 
 constexpr int kMaxSeq = 8;
+constexpr int kLstmThreads = 512;
 
 struct LstmSeqDev {
   const __nv_bfloat16* whh;
@@ -38,10 +44,12 @@ struct LstmParams {
   uint32_t* flags;       // [n_groups][n_seq]
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 template <int BC>
-__global__ void __launch_bounds__(128, 1) lstm_recurrence_kernel(const LstmParams p) {
+__global__ void __launch_bounds__(kLstmThreads, 1) lstm_recurrence_kernel(const LstmParams p) {
+  constexpr int NC = BC / 4;                       // accumulator columns per warp
+  constexpr int XP = NC + 1;                       // padded pitch of the exchange tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -60,8 +68,8 @@ __global__ void __launch_bounds__(128, 1) lstm_recurrence_kernel(const LstmParam
 
   uint8_t* w_smem = smem;                                       // kblocks x 16 KB
   uint8_t* h_smem = w_smem + kblocks * 16384;                   // kblocks x BC*128 B
-  float* xch = reinterpret_cast<float*>(h_smem + kblocks * BC * 128);   // [128][17]
-  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(xch + 128 * 17);
+  float* xch = reinterpret_cast<float*>(h_smem + kblocks * BC * 128);   // [16 warps][32][XP]
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(xch + 16 * 32 * XP);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
   // ---- one-time setup: barrier, TMEM, resident W_hh slice ----
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(128, 1) lstm_recurrence_kernel(const LstmParam
   {
     const int chunks_per_row = H >> 3;
     const uint4* src = reinterpret_cast<const uint4*>(sq.whh + static_cast<size_t>(slice) * 128 * H);
-    for (int e = tid; e < 128 * chunks_per_row; e += 128) {
+    for (int e = tid; e < 128 * chunks_per_row; e += kLstmThreads) {
       const int row = e / chunks_per_row;
       const int cc = e - row * chunks_per_row;
       *reinterpret_cast<uint4*>(w_smem + (cc >> 3) * 16384 + ptx::sw128_offset(row, cc & 7)) = __ldg(src + e);
@@ -91,7 +99,9 @@ __global__ void __launch_bounds__(128, 1) lstm_recurrence_kernel(const LstmParam
 
   const int b0 = group * BC;                       // first chunk of this batch group
   const int nvalid = min(BC, p.B - b0);            // chunks >= nvalid are padding
-  const int r = tid;                               // gate row inside the slice: 4*unit_local + gate
+  const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
+  const int cg = warp >> 2;                        // column group: columns cg*NC .. cg*NC+NC-1
+  const int r = quarter * 32 + lane;               // gate row inside the slice: 4*unit_local + gate
   const int gate = lane & 3;
   const int unit = slice * 32 + (r >> 2);          // hidden unit this thread updates
   const int jlane = lane & 3;                      // batch sub-column this thread updates
@@ -103,21 +113,26 @@ __global__ void __launch_bounds__(128, 1) lstm_recurrence_kernel(const LstmParam
   __nv_bfloat16* hbuf = p.hbuf + static_cast<size_t>(group * p.n_seq + q) * 2 * BC * p.Hmax;
   uint32_t* flag = p.flags + group * p.n_seq + q;
   const float* gx_row = sq.gx + slice * 128 + r;
+  float* xw = xch + warp * 32 * XP;                // warp-private exchange tile
   constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BC);
+  const int chunks_per_row = H >> 3;
+  const int gather_total = BC * chunks_per_row;    // 16-byte chunks of h_{t-1}
 
-  float cstate[BC / 4];
+  float cstate[NC / 4];
 #pragma unroll
-  for (int i = 0; i < BC / 4; ++i) cstate[i] = 0.0f;
+  for (int i = 0; i < NC / 4; ++i) cstate[i] = 0.0f;
   uint32_t parity = 0;
 
   for (int step = 0; step < p.T; ++step) {
     const int t = sq.reverse ? p.T - 1 - step : step;
 
     // prefetch this step's input projections (independent of h_{t-1})
-    float gxv[BC];
+    float gxv[NC];
 #pragma unroll
-    for (int b = 0; b < BC; ++b)
-      gxv[b] = b < nvalid ? __ldg(gx_row + (static_cast<size_t>(b0 + b) * p.T + t) * sq.ld_gx) : 0.0f;
+    for (int j = 0; j < NC; ++j) {
+      const int b = cg * NC + j;
+      gxv[j] = b < nvalid ? __ldg(gx_row + (static_cast<size_t>(b0 + b) * p.T + t) * sq.ld_gx) : 0.0f;
+    }
 
     if (step > 0) {
       if (tid == 0) {
@@ -126,25 +141,23 @@ __global__ void __launch_bounds__(128, 1) lstm_recurrence_kernel(const LstmParam
         }
       }
       __syncthreads();
-      // gather h_{t-1} (BC x H bf16) from L2 into the swizzled B-operand tile
+      // gather h_{t-1} (BC x H bf16) from L2 into the swizzled B-operand tile; up to 4 independent
+      // 16-byte loads in flight per thread before the first dependent smem store
       const uint4* hsrc = reinterpret_cast<const uint4*>(hbuf + static_cast<size_t>((step - 1) & 1) * BC * p.Hmax);
-      const int chunks_per_row = H >> 3;
-      const int total = BC * chunks_per_row;
-      // 8 independent 16-byte L2 loads in flight per thread before the first dependent smem store
-      for (int e0 = tid; e0 < total; e0 += 128 * 8) {
-        uint4 v[8];
+      for (int e0 = tid; e0 < gather_total; e0 += kLstmThreads * 4) {
+        uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * 128;
-          if (e < total) {
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * kLstmThreads;
+          if (e < gather_total) {
             const int row = e / chunks_per_row;
             v[u] = ptx::ld_cg_v4(hsrc + static_cast<size_t>(row) * (p.Hmax >> 3) + (e - row * chunks_per_row));
           }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * 128;
-          if (e < total) {
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * kLstmThreads;
+          if (e < gather_total) {
             const int row = e / chunks_per_row;
             const int cc = e - row * chunks_per_row;
             *reinterpret_cast<uint4*>(h_smem + (cc >> 3) * (BC * 128) + ptx::sw128_offset(row, cc & 7)) = v[u];
@@ -170,46 +183,42 @@ __global__ void __launch_bounds__(128, 1) lstm_recurrence_kernel(const LstmParam
       ptx::tc_fence_after();
     }
 
+    // ---- gates -> activations -> warp-private exchange -> cell update ----
+    uint32_t v[NC];
+    if (step > 0) {
+      ptx::tmem_ld_cols<NC>(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + cg * NC, v);
+      ptx::tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) v[j] = 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const float pre = __uint_as_float(v[j]) + gxv[j];
+      xw[lane * XP + j] = act_a * sigmoid_fast(act_k * pre) + act_c;
+    }
+    __syncwarp();
     __nv_bfloat16* hdst = hbuf + static_cast<size_t>(step & 1) * BC * p.Hmax;
+    const float* g4 = xw + (lane & ~3) * XP;       // rows of this thread's unit: i, f, g, o
 #pragma unroll
-    for (int cc = 0; cc < BC / 16; ++cc) {
-      uint32_t v[16];
-      if (step > 0) {
-        ptx::tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + cc * 16, v);
-        ptx::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0u;
+    for (int m = 0; m < NC / 4; ++m) {
+      const int j = jlane + 4 * m;
+      const float gi = g4[j], gf = g4[XP + j], gg = g4[2 * XP + j], go = g4[3 * XP + j];
+      const float c = gf * cstate[m] + gi * gg;
+      cstate[m] = c;
+      const float h = go * (2.0f * sigmoid_fast(2.0f * c) - 1.0f);
+      const int b = cg * NC + j;
+      const __nv_bfloat16 hb = __float2bfloat16_rn(h);
+      hdst[static_cast<size_t>(b) * p.Hmax + unit] = hb;
+      if (b < nvalid) {
+        const size_t row = static_cast<size_t>(b0 + b) * p.T + t;
+        if (sq.out_bf16) sq.out_bf16[row * sq.ld_out + unit] = hb;
+        if (sq.out_f32) sq.out_f32[row * sq.ld_out32 + unit] = h;
       }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float pre = __uint_as_float(v[j]) + gxv[cc * 16 + j];
-        xch[r * 17 + j] = act_a * sigmoidf_(act_k * pre) + act_c;
-      }
-      __syncwarp();
-      const float* g4 = xch + (r & ~3) * 17;      // rows of this thread's unit: i, f, g, o
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int j = jlane + 4 * m;
-        const float gi = g4[j], gf = g4[17 + j], gg = g4[34 + j], go = g4[51 + j];
-        const float c = gf * cstate[cc * 4 + m] + gi * gg;
-        cstate[cc * 4 + m] = c;
-        const float h = go * (2.0f * sigmoidf_(2.0f * c) - 1.0f);
-        const int b = cc * 16 + j;
-        const __nv_bfloat16 hb = __float2bfloat16_rn(h);
-        hdst[static_cast<size_t>(b) * p.Hmax + unit] = hb;
-        if (b < nvalid) {
-          const size_t row = static_cast<size_t>(b0 + b) * p.T + t;
-          if (sq.out_bf16) sq.out_bf16[row * sq.ld_out + unit] = hb;
-          if (sq.out_f32) sq.out_f32[row * sq.ld_out32 + unit] = h;
-        }
-      }
-      __syncwarp();
     }
 
-    // publish h_t to the sibling slices
-    // bar.sync orders every thread's h stores before thread 0's gpu-scope release (cumulativity),
-    // so no per-thread __threadfence() is needed on this latency-critical path.
+    // publish h_t to the sibling slices.  bar.sync orders every thread's h stores before thread
+    // 0's gpu-scope release (cumulativity), so no per-thread __threadfence() is needed.
     ptx::tc_fence_before();
     __syncthreads();
     if (tid == 0) ptx::red_release_gpu_add(flag, 1u);
@@ -224,7 +233,8 @@ __global__ void __launch_bounds__(128, 1) lstm_recurrence_kernel(const LstmParam
 }
 
 static size_t lstm_smem_bytes(int Hmax, int BC) {
-  return static_cast<size_t>(Hmax / 64) * 16384 + static_cast<size_t>(Hmax / 64) * BC * 128 + 128 * 17 * 4 + 64 + 1024;
+  return static_cast<size_t>(Hmax / 64) * 16384 + static_cast<size_t>(Hmax / 64) * BC * 128 +
+         16 * 32 * (BC / 4 + 1) * 4 + 64 + 1024;
 }
 
 struct LstmPlan {
@@ -269,8 +279,8 @@ static int lstm_launch(const LstmParams& p, int grid, size_t smem, cudaStream_t 
     attr = smem;
   }
   void* args[] = {const_cast<LstmParams*>(&p)};
-  AMT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_recurrence_kernel<BC>), dim3(grid), dim3(128), args,
-                                       smem, stream));
+  AMT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_recurrence_kernel<BC>), dim3(grid),
+                                       dim3(kLstmThreads), args, smem, stream));
   count_launch();
   return 0;
 }
