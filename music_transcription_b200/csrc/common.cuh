@@ -72,6 +72,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp.  Code that feeds the uniform datapath (UTCHMMA / UTMALDG take
+// uniform registers) should be executed by the WHOLE warp with only the issuing instruction
+// predicated on this: a divergent `if (lane == 0)` makes ptxas wrap every such instruction in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~15 SASS instructions per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -22,6 +22,8 @@
 // per-thread fences, 4 warps per scheduler for the transcendental-heavy epilogue.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace amt {
@@ -42,6 +44,7 @@ struct LstmParams {
   int n_seq, ctas_per_group, B, T, n_groups, Hmax;
   __nv_bfloat16* hbuf;   // [n_groups][n_seq][2][BC][Hmax]
   uint32_t* flags;       // [n_groups][n_seq]
+  long long* trace;      // debug: per-phase cycle totals of CTA 0 (AMT_LSTM_TRACE=1), else nullptr
 };
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -118,10 +121,19 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_recurrence_kernel(const 
   const int chunks_per_row = H >> 3;
   const int gather_total = BC * chunks_per_row;    // 16-byte chunks of h_{t-1}
 
+  const bool mma_leader = ptx::elect_one_sync();   // one lane per warp; only warp 0's is used
+  const uint64_t w_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(w_smem));
+  const uint64_t h_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(h_smem));
+
   float cstate[NC / 4];
 #pragma unroll
   for (int i = 0; i < NC / 4; ++i) cstate[i] = 0.0f;
   uint32_t parity = 0;
+
+  long long tr[6] = {0, 0, 0, 0, 0, 0};
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
+#define TRACE_MARK(i) do { if (tracing) { const long long _c = clock64(); tr[i] += _c - tlast; tlast = _c; } } while (0)
+  long long tlast = tracing ? clock64() : 0;
 
   for (int step = 0; step < p.T; ++step) {
     const int t = sq.reverse ? p.T - 1 - step : step;
@@ -141,6 +153,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_recurrence_kernel(const 
         }
       }
       __syncthreads();
+      TRACE_MARK(0);   // gx issue + flag wait
       // gather h_{t-1} (BC x H bf16) from L2 into the swizzled B-operand tile; up to 4 independent
       // 16-byte loads in flight per thread before the first dependent smem store
       const uint4* hsrc = reinterpret_cast<const uint4*>(hbuf + static_cast<size_t>((step - 1) & 1) * BC * p.Hmax);
@@ -166,21 +179,26 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_recurrence_kernel(const 
       }
       ptx::fence_proxy_async_smem();
       __syncthreads();
-      if (tid == 0) {
+      TRACE_MARK(1);   // h gather
+      if (warp == 0) {
+        // whole warp runs the uniform loop, one elected lane issues (keeps descriptors in uniform
+        // registers: ~3 SASS instructions per MMA instead of an ELECT/BRA.U.ANY loop each)
         ptx::tc_fence_after();
-        const uint32_t wa = ptx::smem_u32(w_smem);
-        const uint32_t ha = ptx::smem_u32(h_smem);
-        for (int kb = 0; kb < kblocks; ++kb) {
+        if (mma_leader) {
+          for (int kb = 0; kb < kblocks; ++kb) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_ss(tmem_base, ptx::umma_desc_sw128(wa + kb * 16384 + k * 32),
-                              ptx::umma_desc_sw128(ha + kb * (BC * 128) + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16_ss(tmem_base, w_desc0 + static_cast<uint64_t>(kb * 1024 + 2 * k),
+                                h_desc0 + static_cast<uint64_t>(kb * (BC * 8) + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(mma_bar);
         }
-        ptx::umma_commit(mma_bar);
+        __syncwarp();
       }
       ptx::mbar_wait(mma_bar, parity);
       parity ^= 1;
       ptx::tc_fence_after();
+      TRACE_MARK(2);   // MMA issue + completion
     }
 
     // ---- gates -> activations -> warp-private exchange -> cell update ----
@@ -220,9 +238,15 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_recurrence_kernel(const 
     // publish h_t to the sibling slices.  bar.sync orders every thread's h stores before thread
     // 0's gpu-scope release (cumulativity), so no per-thread __threadfence() is needed.
     ptx::tc_fence_before();
+    TRACE_MARK(3);     // epilogue of this thread
     __syncthreads();
+    TRACE_MARK(4);     // wait for the slowest warp
     if (tid == 0) ptx::red_release_gpu_add(flag, 1u);
+    TRACE_MARK(5);     // release
   }
+  if (tracing)
+    for (int i = 0; i < 6; ++i) p.trace[i] = tr[i];
+#undef TRACE_MARK
 
   ptx::tc_fence_before();
   __syncthreads();
@@ -323,11 +347,24 @@ int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, s
     p.flags = static_cast<uint32_t*>(scratch);
     p.hbuf = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(scratch) + plan.flags_bytes);
     AMT_CUDA(cudaMemsetAsync(p.flags, 0, plan.flags_bytes, stream));
+    static const bool trace_on = getenv("AMT_LSTM_TRACE") != nullptr;
+    long long* trace_dev = nullptr;
+    if (trace_on) AMT_CUDA(cudaMalloc(&trace_dev, 6 * sizeof(long long)));
+    p.trace = trace_dev;
     const int grid = p.n_groups * plan.ctas_per_group;
     const size_t smem = lstm_smem_bytes(plan.Hmax, plan.BC);
     if (plan.BC == 16) AMT_TRY(lstm_launch<16>(p, grid, smem, stream));
     else if (plan.BC == 32) AMT_TRY(lstm_launch<32>(p, grid, smem, stream));
     else AMT_TRY(lstm_launch<64>(p, grid, smem, stream));
+    if (trace_on) {   // debug only: host sync + print
+      long long h[6];
+      AMT_CUDA(cudaStreamSynchronize(stream));
+      AMT_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+      cudaFree(trace_dev);
+      fprintf(stderr, "[lstm trace] n_seq=%d BC=%d grid=%d T=%d cycles/step: wait %.0f gather %.0f mma %.0f epi %.0f barrier %.0f release %.0f\n",
+              n_seq, plan.BC, grid, T, (double)h[0] / T, (double)h[1] / T, (double)h[2] / T, (double)h[3] / T,
+              (double)h[4] / T, (double)h[5] / T);
+    }
   }
   return 0;
 }

@@ -90,62 +90,76 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int m = tile / p.n_tiles;
-        const int n0 = (tile - m * p.n_tiles) * BN;
-        const int f0 = (m % p.tilesF) * boxF;
-        m /= p.tilesF;
-        const int t0 = (m % p.tilesT) * p.boxT;
-        const int b = m / p.tilesT;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const uint32_t s = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1;
-          ptx::mbar_wait(&empty[s], ph ^ 1);
+    // The whole warp runs the (warp-uniform) loop; only the issuing instructions are predicated on
+    // one elected lane, so coordinates / addresses stay in uniform registers.
+    const bool leader = ptx::elect_one_sync();
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int m = tile / p.n_tiles;
+      const int n0 = (tile - m * p.n_tiles) * BN;
+      const int f0 = (m % p.tilesF) * boxF;
+      m /= p.tilesF;
+      const int t0 = (m % p.tilesT) * p.boxT;
+      const int b = m / p.tilesT;
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const uint32_t s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* a_dst = smem + s * Cfg::kStageBytes;
+        uint8_t* b_dst = a_dst + kABytes;
+        int c0, c1, c2;
+        const CUtensorMap* am;
+        if (kb < p.kblocks0) {
+          const int tap = kb / p.cblk0;
+          const int kf = tap / p.ntapT;
+          c0 = (kb - tap * p.cblk0) * kBlockK;
+          c1 = f0 + kf - p.padF;
+          c2 = t0 + (tap - kf * p.ntapT) - p.padT;
+          am = &tmA0;
+        } else {
+          c0 = (kb - p.kblocks0) * kBlockK;
+          c1 = f0;
+          c2 = t0;
+          am = &tmA1;
+        }
+        if (leader) {
           ptx::mbar_expect_tx(&full[s], Cfg::kStageBytes);
-          uint8_t* a_dst = smem + s * Cfg::kStageBytes;
-          uint8_t* b_dst = a_dst + kABytes;
-          if (kb < p.kblocks0) {
-            const int tap = kb / p.cblk0;
-            const int cb = kb - tap * p.cblk0;
-            const int kf = tap / p.ntapT;
-            const int kt = tap - kf * p.ntapT;
-            ptx::tma_load_4d(a_dst, &tmA0, &full[s], cb * kBlockK, f0 + kf - p.padF, t0 + kt - p.padT, b);
-          } else {
-            ptx::tma_load_4d(a_dst, &tmA1, &full[s], (kb - p.kblocks0) * kBlockK, f0, t0, b);
-          }
+          ptx::tma_load_4d(a_dst, am, &full[s], c0, c1, c2, b);
           ptx::tma_load_2d(b_dst, &tmB, &full[s], kb * kBlockK, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, BN);
-      uint32_t it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1;
-        const uint32_t aph = (tl >> 1) & 1;
-        ptx::mbar_wait(&tempty[acc], aph ^ 1);
+    const bool leader = ptx::elect_one_sync();
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, BN);
+    const uint64_t desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smem));     // stage 0, A tile, k = 0
+    uint32_t it = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      const uint32_t acc = tl & 1;
+      const uint32_t aph = (tl >> 1) & 1;
+      ptx::mbar_wait(&tempty[acc], aph ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const uint32_t s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1;
+        ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const uint32_t s = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1;
-          ptx::mbar_wait(&full[s], ph);
-          ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem + s * Cfg::kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
+        // descriptors differ only in the 14-bit start-address field (units of 16 bytes)
+        const uint64_t a_desc = desc0 + static_cast<uint64_t>((s * Cfg::kStageBytes) >> 4);
+        const uint64_t b_desc = a_desc + static_cast<uint64_t>(kABytes >> 4);
+        if (leader) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_sw128(a_addr + k * 32), ptx::umma_desc_sw128(b_addr + k * 32),
-                              idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBlockK / 16; ++k)
+            ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           ptx::umma_commit(&empty[s]);   // frees the smem slot once these MMAs retire
         }
-        ptx::umma_commit(&tfull[acc]);   // accumulator ready for the epilogue
+        __syncwarp();
       }
+      if (leader) ptx::umma_commit(&tfull[acc]);   // accumulator ready for the epilogue
+      __syncwarp();
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
