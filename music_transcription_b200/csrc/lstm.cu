@@ -24,6 +24,8 @@
 
 #include <cstdlib>
 
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace amt {
@@ -295,6 +297,338 @@ static int lstm_plan(const amt_lstm_seq* seqs, int n_seq, int B, LstmPlan* plan)
   return 0;
 }
 
+// ============================================================================
+// Cluster variant: the slices of one sequence form (part of) a thread-block cluster and
+// exchange h_t through distributed shared memory instead of L2.  Per step every CTA stages
+// its 32 x BC new h values in its own smem, pushes them with 16-byte st.shared::cluster
+// stores straight into the (double-buffered, swizzled) B-operand tile of every peer, and
+// arrives (release.cluster) on the peer's mbarrier; the consumer waits (acquire.cluster) for
+// n_peers arrivals.  No L2 round trips, no spinning on global memory, no cooperative launch:
+// clusters are co-scheduled by hardware and independent of each other.
+// ============================================================================
+constexpr int kMaxClusterCtas = 64;     // CTAs of one batch group (all its clusters)
+
+struct LstmClusterParams {
+  LstmSeqDev seq[kMaxSeq];
+  int n_seq, ctas_per_group, B, T, cluster_size;
+  unsigned char cta_seq[kMaxClusterCtas];     // sequence hosted by CTA w of a group (255 = idle padding)
+  unsigned char cta_slice[kMaxClusterCtas];   // its slice of 32 hidden units
+  unsigned char cta_peer0[kMaxClusterCtas];   // cluster rank of slice 0 of that sequence
+  long long* trace;
+};
+
+template <int BC>
+__global__ void __launch_bounds__(kLstmThreads, 1) lstm_cluster_kernel(const LstmClusterParams p) {
+  constexpr int NC = BC / 4;
+  constexpr int XP = NC + 1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int group = blockIdx.x / p.ctas_per_group;
+  const int within = blockIdx.x - group * p.ctas_per_group;
+  const int q = p.cta_seq[within];
+  const bool idle = q == 255;
+  const LstmSeqDev sq = p.seq[idle ? 0 : q];
+  const int slice = p.cta_slice[within];
+  const int peer0 = p.cta_peer0[within];
+  const int H = sq.H;
+  const int n_peers = sq.n_slices;
+  const int kblocks = H >> 6;
+  const int hbuf_bytes = kblocks * BC * 128;
+
+  uint8_t* w_smem = smem;                                         // kblocks x 16 KB   resident W_hh slice
+  uint8_t* h_smem = w_smem + kblocks * 16384;                     // 2 x hbuf_bytes    B operand, double buffered
+  float* xch = reinterpret_cast<float*>(h_smem + 2 * hbuf_bytes); // [16 warps][32][XP]
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(xch + 16 * 32 * XP);   // [BC][32] new h of this slice
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(stage + BC * 32);
+  uint64_t* hbar = mma_bar + 1;                                   // [2]: h tile buffer complete (n_peers arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hbar + 2);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_init(mma_bar, 1);
+      ptx::mbar_init(&hbar[0], n_peers);
+      ptx::mbar_init(&hbar[1], n_peers);
+      ptx::mbar_fence_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, BC < 32 ? 32 : BC);
+    ptx::tmem_relinquish();
+  }
+  if (!idle) {
+    const int chunks_per_row = H >> 3;
+    const uint4* src = reinterpret_cast<const uint4*>(sq.whh + static_cast<size_t>(slice) * 128 * H);
+    for (int e = tid; e < 128 * chunks_per_row; e += kLstmThreads) {
+      const int row = e / chunks_per_row;
+      const int cc = e - row * chunks_per_row;
+      *reinterpret_cast<uint4*>(w_smem + (cc >> 3) * 16384 + ptx::sw128_offset(row, cc & 7)) = __ldg(src + e);
+    }
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::cluster_sync_all();            // every peer's mbarriers are initialised before any remote arrive
+
+  if (!idle) {
+    const int b0 = group * BC;
+    const int nvalid = min(BC, p.B - b0);
+    const int quarter = warp & 3;
+    const int cg = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const int gate = lane & 3;
+    const int ul = r >> 2;                           // unit inside the slice
+    const int unit = slice * 32 + ul;
+    const int jlane = lane & 3;
+    const float act_k = gate == 2 ? 2.0f : 1.0f;
+    const float act_a = gate == 2 ? 2.0f : 1.0f;
+    const float act_c = gate == 2 ? -1.0f : 0.0f;
+    const float* gx_row = sq.gx + slice * 128 + r;
+    float* xw = xch + warp * 32 * XP;
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BC);
+    const bool mma_leader = ptx::elect_one_sync();
+    const uint64_t w_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(w_smem));
+    const uint64_t h_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(h_smem));
+    const uint32_t h_smem_u = ptx::smem_u32(h_smem);
+    const uint32_t hbar_u = ptx::smem_u32(hbar);
+    const int push_total = n_peers * BC * 4;         // 16-byte chunks pushed per step
+
+    float cstate[NC / 4];
+#pragma unroll
+    for (int i = 0; i < NC / 4; ++i) cstate[i] = 0.0f;
+    uint32_t parity = 0;
+
+    long long tr[6] = {0, 0, 0, 0, 0, 0};
+    const bool tracing = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
+#define TRACE_MARK(i) do { if (tracing) { const long long _c = clock64(); tr[i] += _c - tlast; tlast = _c; } } while (0)
+    long long tlast = tracing ? clock64() : 0;
+
+    for (int step = 0; step < p.T; ++step) {
+      const int t = sq.reverse ? p.T - 1 - step : step;
+      float gxv[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int b = cg * NC + j;
+        gxv[j] = b < nvalid ? __ldg(gx_row + (static_cast<size_t>(b0 + b) * p.T + t) * sq.ld_gx) : 0.0f;
+      }
+
+      if (step > 0) {
+        const int buf = (step - 1) & 1;
+        ptx::mbar_wait_acquire_cluster(&hbar[buf], ((step - 1) >> 1) & 1);     // h_{t-1} from all peers has landed
+        TRACE_MARK(0);
+        if (warp == 0) {
+          ptx::fence_proxy_async_smem();      // peers' generic-proxy writes -> async-proxy (UMMA) reads
+          ptx::tc_fence_after();
+          if (mma_leader) {
+            const uint64_t hd = h_desc0 + static_cast<uint64_t>((buf * hbuf_bytes) >> 4);
+            for (int kb = 0; kb < kblocks; ++kb) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::umma_bf16_ss(tmem_base, w_desc0 + static_cast<uint64_t>(kb * 1024 + 2 * k),
+                                  hd + static_cast<uint64_t>(kb * (BC * 8) + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit(mma_bar);
+          }
+          __syncwarp();
+        }
+        ptx::mbar_wait(mma_bar, parity);
+        parity ^= 1;
+        ptx::tc_fence_after();
+        TRACE_MARK(1);
+      }
+
+      uint32_t v[NC];
+      if (step > 0) {
+        ptx::tmem_ld_cols<NC>(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + cg * NC, v);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) v[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const float pre = __uint_as_float(v[j]) + gxv[j];
+        xw[lane * XP + j] = act_a * sigmoid_fast(act_k * pre) + act_c;
+      }
+      __syncwarp();
+      const float* g4 = xw + (lane & ~3) * XP;
+#pragma unroll
+      for (int m = 0; m < NC / 4; ++m) {
+        const int j = jlane + 4 * m;
+        const float gi = g4[j], gf = g4[XP + j], gg = g4[2 * XP + j], go = g4[3 * XP + j];
+        const float c = gf * cstate[m] + gi * gg;
+        cstate[m] = c;
+        const float h = go * (2.0f * sigmoid_fast(2.0f * c) - 1.0f);
+        const int b = cg * NC + j;
+        const __nv_bfloat16 hb = __float2bfloat16_rn(h);
+        stage[b * 32 + ul] = hb;
+        if (b < nvalid) {
+          const size_t row = static_cast<size_t>(b0 + b) * p.T + t;
+          if (sq.out_bf16) sq.out_bf16[row * sq.ld_out + unit] = hb;
+          if (sq.out_f32) sq.out_f32[row * sq.ld_out32 + unit] = h;
+        }
+      }
+      ptx::tc_fence_before();
+      __syncthreads();                 // staging tile complete; all TMEM reads of this step retired
+      TRACE_MARK(2);
+
+      // push this slice's h_t (BC x 32 bf16) into buffer step&1 of every peer's B-operand tile
+      {
+        const int buf = step & 1;
+        for (int e = tid; e < push_total; e += kLstmThreads) {
+          const int peer = e / (BC * 4);
+          const int rem = e - peer * (BC * 4);
+          const int b = rem >> 2, c = rem & 3;
+          const uint4 val = *reinterpret_cast<const uint4*>(stage + b * 32 + c * 8);
+          const int unit0 = slice * 32 + c * 8;
+          const uint32_t off = buf * hbuf_bytes + (unit0 >> 6) * (BC * 128) + ptx::sw128_offset(b, (unit0 & 63) >> 3);
+          ptx::st_cluster_v4(ptx::mapa(h_smem_u + off, peer0 + peer), val);
+        }
+        __syncthreads();               // every thread's pushes precede the arrives below (cumulativity)
+        if (tid < n_peers) ptx::mbar_arrive_remote_release(ptx::mapa(hbar_u + buf * 8, peer0 + tid));
+      }
+      TRACE_MARK(3);
+    }
+    if (tracing)
+      for (int i = 0; i < 6; ++i) p.trace[i] = tr[i];
+#undef TRACE_MARK
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();             // no CTA exits while a peer may still push into its smem
+  if (warp == 0) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, BC < 32 ? 32 : BC);
+  }
+}
+
+static size_t lstm_cluster_smem_bytes(int Hmax, int BC) {
+  return static_cast<size_t>(Hmax / 64) * 16384 + 2 * static_cast<size_t>(Hmax / 64) * BC * 128 +
+         16 * 32 * (BC / 4 + 1) * 4 + static_cast<size_t>(BC) * 64 + 64 + 1024;
+}
+
+struct ClusterPlan {
+  bool ok;
+  int BC, CS, ctas_per_group, Hmax;
+  unsigned char cta_seq[kMaxClusterCtas], cta_slice[kMaxClusterCtas], cta_peer0[kMaxClusterCtas];
+};
+
+template <int BC>
+static int lstm_cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int grid, int CS, size_t smem,
+                               cudaStream_t stream) {
+  static size_t attr_smem = 0;
+  static bool nonportable = false;
+  if (smem > attr_smem) {
+    AMT_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  if (CS > 8 && !nonportable) {
+    AMT_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<BC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    nonportable = true;
+  }
+  *cfg = cudaLaunchConfig_t{};
+  cfg->gridDim = dim3(grid);
+  cfg->blockDim = dim3(kLstmThreads);
+  cfg->dynamicSmemBytes = smem;
+  cfg->stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+  return 0;
+}
+
+template <int BC>
+static int lstm_cluster_max_active(int CS, size_t smem, int* out) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  AMT_TRY(lstm_cluster_config<BC>(&cfg, attr, CS, CS, smem, nullptr));
+  int n = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, lstm_cluster_kernel<BC>, &cfg);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *out = n;
+  return 0;
+}
+
+template <int BC>
+static int lstm_cluster_launch(const LstmClusterParams& p, int grid, int CS, size_t smem, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  AMT_TRY(lstm_cluster_config<BC>(&cfg, attr, grid, CS, smem, stream));
+  AMT_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<BC>, p));
+  count_launch();
+  return 0;
+}
+
+// Pack sequences into clusters of CS = max(n_slices): a sequence with CS slices fills a cluster,
+// smaller sequences of equal H share one (e.g. the two directions of the local LSTM).
+static int lstm_cluster_plan(const amt_lstm_seq* seqs, int n_seq, int B, ClusterPlan* plan) {
+  plan->ok = false;
+  int CS = 0, Hmax = 0;
+  for (int i = 0; i < n_seq; ++i) {
+    if (seqs[i].H % 64 != 0 || seqs[i].H < 64) return 0;
+    CS = std::max(CS, seqs[i].H / 32);
+    Hmax = std::max(Hmax, seqs[i].H);
+  }
+  if (CS > 16) return 0;
+  int n_ctas = 0;
+  bool placed[kMaxSeq] = {false};
+  for (int i = 0; i < n_seq; ++i) {
+    if (placed[i]) continue;
+    int rank = 0;
+    for (int j = i; j < n_seq; ++j) {           // fill this cluster with sequences of the same H
+      if (placed[j] || seqs[j].H != seqs[i].H) continue;
+      const int ns = seqs[j].H / 32;
+      if (rank + ns > CS) break;
+      if (n_ctas + rank + ns > kMaxClusterCtas) return 0;
+      for (int s = 0; s < ns; ++s) {
+        plan->cta_seq[n_ctas + rank + s] = static_cast<unsigned char>(j);
+        plan->cta_slice[n_ctas + rank + s] = static_cast<unsigned char>(s);
+        plan->cta_peer0[n_ctas + rank + s] = static_cast<unsigned char>(rank);
+      }
+      rank += ns;
+      placed[j] = true;
+    }
+    for (; rank < CS; ++rank) {                 // idle padding
+      if (n_ctas + rank >= kMaxClusterCtas) return 0;
+      plan->cta_seq[n_ctas + rank] = 255;
+      plan->cta_slice[n_ctas + rank] = 0;
+      plan->cta_peer0[n_ctas + rank] = 0;
+    }
+    n_ctas += CS;
+    if (n_ctas > kMaxClusterCtas) return 0;
+  }
+  const int clusters_per_group = n_ctas / CS;
+  int BC = 0;
+  for (int cand : {16, 32, 64}) {
+    const size_t smem = lstm_cluster_smem_bytes(Hmax, cand);
+    if (smem > 227 * 1024) break;
+    int max_active = 0;
+    if (cand == 16) AMT_TRY(lstm_cluster_max_active<16>(CS, smem, &max_active));
+    else if (cand == 32) AMT_TRY(lstm_cluster_max_active<32>(CS, smem, &max_active));
+    else AMT_TRY(lstm_cluster_max_active<64>(CS, smem, &max_active));
+    if (max_active < 1) break;
+    BC = cand;
+    if (ceil_div(B, cand) * clusters_per_group <= max_active) break;   // everything co-resident
+  }
+  if (BC == 0) return 0;
+  plan->ok = true;
+  plan->BC = BC;
+  plan->CS = CS;
+  plan->ctas_per_group = n_ctas;
+  plan->Hmax = Hmax;
+  return 0;
+}
+
 template <int BC>
 static int lstm_launch(const LstmParams& p, int grid, size_t smem, cudaStream_t stream) {
   static size_t attr = 0;
@@ -312,6 +646,53 @@ static int lstm_launch(const LstmParams& p, int grid, size_t smem, cudaStream_t 
 int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, size_t scratch_bytes,
              cudaStream_t stream) {
   AMT_TRY(ensure_device());
+  AMT_REQUIRE(n_seq >= 1 && n_seq <= kMaxSeq && B >= 1 && T >= 1, "lstm: bad sizes");
+  static const bool trace_on = getenv("AMT_LSTM_TRACE") != nullptr;
+  static const bool force_l2 = getenv("AMT_LSTM_L2") != nullptr;
+  ClusterPlan cp;
+  AMT_TRY(lstm_cluster_plan(seqs, n_seq, B, &cp));
+  if (cp.ok && !force_l2) {
+    LstmClusterParams p{};
+    for (int i = 0; i < n_seq; ++i) {
+      LstmSeqDev& s = p.seq[i];
+      s.whh = static_cast<const __nv_bfloat16*>(seqs[i].whh);
+      s.gx = seqs[i].gx;
+      s.out_bf16 = static_cast<__nv_bfloat16*>(seqs[i].out_bf16);
+      s.out_f32 = seqs[i].out_f32;
+      s.H = seqs[i].H;
+      s.reverse = seqs[i].reverse;
+      s.ld_gx = seqs[i].ld_gx;
+      s.ld_out = seqs[i].ld_out;
+      s.ld_out32 = seqs[i].ld_out32;
+      s.n_slices = seqs[i].H / 32;
+      s.cta_begin = 0;
+    }
+    p.n_seq = n_seq;
+    p.ctas_per_group = cp.ctas_per_group;
+    p.B = B;
+    p.T = T;
+    p.cluster_size = cp.CS;
+    memcpy(p.cta_seq, cp.cta_seq, sizeof(p.cta_seq));
+    memcpy(p.cta_slice, cp.cta_slice, sizeof(p.cta_slice));
+    memcpy(p.cta_peer0, cp.cta_peer0, sizeof(p.cta_peer0));
+    long long* trace_dev = nullptr;
+    if (trace_on) AMT_CUDA(cudaMalloc(&trace_dev, 6 * sizeof(long long)));
+    p.trace = trace_dev;
+    const int grid = ceil_div(B, cp.BC) * cp.ctas_per_group;
+    const size_t smem = lstm_cluster_smem_bytes(cp.Hmax, cp.BC);
+    if (cp.BC == 16) AMT_TRY(lstm_cluster_launch<16>(p, grid, cp.CS, smem, stream));
+    else if (cp.BC == 32) AMT_TRY(lstm_cluster_launch<32>(p, grid, cp.CS, smem, stream));
+    else AMT_TRY(lstm_cluster_launch<64>(p, grid, cp.CS, smem, stream));
+    if (trace_on) {   // debug only: host sync + print
+      long long h[6];
+      AMT_CUDA(cudaStreamSynchronize(stream));
+      AMT_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+      cudaFree(trace_dev);
+      fprintf(stderr, "[lstm cluster trace] n_seq=%d BC=%d CS=%d grid=%d T=%d cycles/step: wait %.0f mma %.0f epilogue %.0f push %.0f\n",
+              n_seq, cp.BC, cp.CS, grid, T, (double)h[0] / T, (double)h[1] / T, (double)h[2] / T, (double)h[3] / T);
+    }
+    return 0;
+  }
   LstmPlan plan;
   AMT_TRY(lstm_plan(seqs, n_seq, B, &plan));
   AMT_REQUIRE(T >= 1, "lstm: T must be >= 1");
@@ -347,7 +728,6 @@ int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, s
     p.flags = static_cast<uint32_t*>(scratch);
     p.hbuf = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(scratch) + plan.flags_bytes);
     AMT_CUDA(cudaMemsetAsync(p.flags, 0, plan.flags_bytes, stream));
-    static const bool trace_on = getenv("AMT_LSTM_TRACE") != nullptr;
     long long* trace_dev = nullptr;
     if (trace_on) AMT_CUDA(cudaMalloc(&trace_dev, 6 * sizeof(long long)));
     p.trace = trace_dev;
