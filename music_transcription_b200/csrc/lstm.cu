@@ -314,11 +314,14 @@ struct LstmClusterParams {
   unsigned char cta_seq[kMaxClusterCtas];     // sequence hosted by CTA w of a group (255 = idle padding)
   unsigned char cta_slice[kMaxClusterCtas];   // its slice of 32 hidden units
   unsigned char cta_peer0[kMaxClusterCtas];   // cluster rank of slice 0 of that sequence
+  __nv_bfloat16* hglob;  // [slots = groups*n_seq*2][BC][Hmax] bf16: h_t staging in global memory (L2 resident)
+  int Hmax;
   long long* trace;
 };
 
 template <int BC>
-__global__ void __launch_bounds__(kLstmThreads, 1) lstm_cluster_kernel(const LstmClusterParams p) {
+__global__ void __launch_bounds__(kLstmThreads, 1)
+lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterParams p) {
   constexpr int NC = BC / 4;
   constexpr int XP = NC + 1;
   extern __shared__ uint8_t smem_raw[];
@@ -350,8 +353,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_cluster_kernel(const Lst
   if (warp == 0) {
     if (lane == 0) {
       ptx::mbar_init(mma_bar, 1);
-      ptx::mbar_init(&hbar[0], n_peers);
-      ptx::mbar_init(&hbar[1], n_peers);
+      ptx::mbar_init(&hbar[0], 1);
+      ptx::mbar_init(&hbar[1], 1);
+      ptx::prefetch_tmap(&tmH);
       ptx::mbar_fence_init();
     }
     __syncwarp();
@@ -393,9 +397,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_cluster_kernel(const Lst
     const bool mma_leader = ptx::elect_one_sync();
     const uint64_t w_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(w_smem));
     const uint64_t h_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(h_smem));
-    const uint32_t h_smem_u = ptx::smem_u32(h_smem);
-    const uint32_t hbar_u = ptx::smem_u32(hbar);
-    const int push_total = n_peers * BC * 4;         // 16-byte chunks pushed per step
+    const uint16_t peer_mask = static_cast<uint16_t>(((1u << n_peers) - 1u) << peer0);
 
     float cstate[NC / 4];
 #pragma unroll
@@ -418,10 +420,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_cluster_kernel(const Lst
 
       if (step > 0) {
         const int buf = (step - 1) & 1;
-        ptx::mbar_wait_acquire_cluster(&hbar[buf], ((step - 1) >> 1) & 1);     // h_{t-1} from all peers has landed
+        ptx::mbar_wait(&hbar[buf], ((step - 1) >> 1) & 1);     // all K blocks of h_{t-1} have landed (TMA complete_tx)
         TRACE_MARK(0);
         if (warp == 0) {
-          ptx::fence_proxy_async_smem();      // peers' generic-proxy writes -> async-proxy (UMMA) reads
           ptx::tc_fence_after();
           if (mma_leader) {
             const uint64_t hd = h_desc0 + static_cast<uint64_t>((buf * hbuf_bytes) >> 4);
@@ -476,30 +477,38 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_cluster_kernel(const Lst
       __syncthreads();                 // staging tile complete; all TMEM reads of this step retired
       TRACE_MARK(2);
 
-      // push this slice's h_t (BC x 32 bf16) into buffer step&1 of every peer's B-operand tile
+      // publish h_t: this slice's BC x 32 bf16 go to global (64-byte rows, L2 resident); after a cluster
+      // barrier the first `kblocks` slices each fetch one 64-unit K block of the assembled BC x H matrix
+      // with ONE multicast TMA that lands in buffer step&1 of every peer's swizzled B-operand tile.
       {
         const int buf = step & 1;
-        for (int e = tid; e < push_total; e += kLstmThreads) {
-          const int peer = e / (BC * 4);
-          const int rem = e - peer * (BC * 4);
-          const int b = rem >> 2, c = rem & 3;
+        const int slot = (group * p.n_seq + q) * 2 + buf;
+        if (tid < BC * 4) {
+          const int b = tid >> 2, c = tid & 3;
           const uint4 val = *reinterpret_cast<const uint4*>(stage + b * 32 + c * 8);
-          const int unit0 = slice * 32 + c * 8;
-          const uint32_t off = buf * hbuf_bytes + (unit0 >> 6) * (BC * 128) + ptx::sw128_offset(b, (unit0 & 63) >> 3);
-          ptx::st_cluster_v4(ptx::mapa(h_smem_u + off, peer0 + peer), val);
+          *reinterpret_cast<uint4*>(p.hglob + (static_cast<size_t>(slot) * BC + b) * p.Hmax + slice * 32 + c * 8) = val;
+          ptx::fence_proxy_async_all();      // generic-proxy global writes -> later async-proxy (TMA) reads
         }
-        __syncthreads();               // every thread's pushes precede the arrives below (cumulativity)
-        if (tid < n_peers) ptx::mbar_arrive_remote_release(ptx::mapa(hbar_u + buf * 8, peer0 + tid));
+        ptx::cluster_sync_all();             // release/acquire: every slice's rows are visible cluster-wide
+        TRACE_MARK(3);
+        if (tid == 0) {
+          ptx::mbar_expect_tx(&hbar[buf], static_cast<uint32_t>(hbuf_bytes));
+          if (slice < kblocks)
+            ptx::tma_load_3d_multicast(h_smem + buf * hbuf_bytes + slice * (BC * 128), &tmH, &hbar[buf], slice * 64, 0, slot,
+                                       peer_mask);
+        }
       }
       TRACE_MARK(3);
     }
     if (tracing)
       for (int i = 0; i < 6; ++i) p.trace[i] = tr[i];
 #undef TRACE_MARK
+  } else {
+    for (int step = 0; step < p.T; ++step) ptx::cluster_sync_all();   // padding CTA: keep the cluster barrier count
   }
 
   ptx::tc_fence_before();
-  ptx::cluster_sync_all();             // no CTA exits while a peer may still push into its smem
+  ptx::cluster_sync_all();             // no CTA exits while a peer's multicast may still target its smem
   if (warp == 0) {
     __syncwarp();
     ptx::tmem_dealloc(tmem_base, BC < 32 ? 32 : BC);
@@ -560,11 +569,12 @@ static int lstm_cluster_max_active(int CS, size_t smem, int* out) {
 }
 
 template <int BC>
-static int lstm_cluster_launch(const LstmClusterParams& p, int grid, int CS, size_t smem, cudaStream_t stream) {
+static int lstm_cluster_launch(const CUtensorMap& tm, const LstmClusterParams& p, int grid, int CS, size_t smem,
+                               cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   AMT_TRY(lstm_cluster_config<BC>(&cfg, attr, grid, CS, smem, stream));
-  AMT_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<BC>, p));
+  AMT_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<BC>, tm, p));
   count_launch();
   return 0;
 }
@@ -678,17 +688,30 @@ int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, s
     long long* trace_dev = nullptr;
     if (trace_on) AMT_CUDA(cudaMalloc(&trace_dev, 6 * sizeof(long long)));
     p.trace = trace_dev;
-    const int grid = ceil_div(B, cp.BC) * cp.ctas_per_group;
+    const int n_groups = ceil_div(B, cp.BC);
+    const int grid = n_groups * cp.ctas_per_group;
     const size_t smem = lstm_cluster_smem_bytes(cp.Hmax, cp.BC);
-    if (cp.BC == 16) AMT_TRY(lstm_cluster_launch<16>(p, grid, cp.CS, smem, stream));
-    else if (cp.BC == 32) AMT_TRY(lstm_cluster_launch<32>(p, grid, cp.CS, smem, stream));
-    else AMT_TRY(lstm_cluster_launch<64>(p, grid, cp.CS, smem, stream));
+    const size_t slots = static_cast<size_t>(n_groups) * n_seq * 2;
+    const size_t need = slots * cp.BC * cp.Hmax * 2;
+    if (scratch_bytes < need) return set_error(AMT_ERR_WORKSPACE, "lstm: scratch %zu < %zu bytes", scratch_bytes, need);
+    p.hglob = static_cast<__nv_bfloat16*>(scratch);
+    p.Hmax = cp.Hmax;
+    CUtensorMap tm;
+    {
+      uint64_t dims[3] = {(uint64_t)cp.Hmax, (uint64_t)cp.BC, (uint64_t)slots};
+      uint64_t str[2] = {(uint64_t)cp.Hmax * 2, (uint64_t)cp.BC * cp.Hmax * 2};
+      uint32_t box[3] = {64, (uint32_t)cp.BC, 1};
+      AMT_TRY(encode_tmap_bf16(&tm, scratch, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    }
+    if (cp.BC == 16) AMT_TRY(lstm_cluster_launch<16>(tm, p, grid, cp.CS, smem, stream));
+    else if (cp.BC == 32) AMT_TRY(lstm_cluster_launch<32>(tm, p, grid, cp.CS, smem, stream));
+    else AMT_TRY(lstm_cluster_launch<64>(tm, p, grid, cp.CS, smem, stream));
     if (trace_on) {   // debug only: host sync + print
       long long h[6];
       AMT_CUDA(cudaStreamSynchronize(stream));
       AMT_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
       cudaFree(trace_dev);
-      fprintf(stderr, "[lstm cluster trace] n_seq=%d BC=%d CS=%d grid=%d T=%d cycles/step: wait %.0f mma %.0f epilogue %.0f push %.0f\n",
+      fprintf(stderr, "[lstm cluster trace] n_seq=%d BC=%d CS=%d grid=%d T=%d cycles/step: tma-wait %.0f mma %.0f epilogue %.0f publish+cluster-barrier %.0f\n",
               n_seq, cp.BC, cp.CS, grid, T, (double)h[0] / T, (double)h[1] / T, (double)h[2] / T, (double)h[3] / T);
     }
     return 0;
@@ -752,7 +775,9 @@ int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, s
 size_t lstm_scratch_bytes(const amt_lstm_seq* seqs, int n_seq, int B) {
   LstmPlan plan;
   if (lstm_plan(seqs, n_seq, B, &plan) != 0) return 0;
-  return plan.flags_bytes + plan.hbuf_bytes;
+  // cluster path: [groups*n_seq*2][BC][Hmax] bf16 with groups*BC <= B + 63
+  const size_t cluster_need = static_cast<size_t>(B + 64) * n_seq * 2 * plan.Hmax * 2;
+  return std::max(plan.flags_bytes + plan.hbuf_bytes, cluster_need) + 1024;
 }
 
 }  // namespace amt
