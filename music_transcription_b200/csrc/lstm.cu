@@ -307,6 +307,8 @@ static int lstm_plan(const amt_lstm_seq* seqs, int n_seq, int B, LstmPlan* plan)
 // clusters are co-scheduled by hardware and independent of each other.
 // ============================================================================
 constexpr int kMaxClusterCtas = 64;     // CTAs of one batch group (all its clusters)
+constexpr int kWCol0 = 64;              // TMEM columns [0,64): accumulator D; [64, 64 + H/2): W_hh slice
+constexpr int kTmemColsCluster = 512;
 
 struct LstmClusterParams {
   LstmSeqDev seq[kMaxSeq];
@@ -342,8 +344,10 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
   const int kblocks = H >> 6;
   const int hbuf_bytes = kblocks * BC * 128;
 
-  uint8_t* w_smem = smem;                                         // kblocks x 16 KB   resident W_hh slice
-  uint8_t* h_smem = w_smem + kblocks * 16384;                     // 2 x hbuf_bytes    B operand, double buffered
+  // W_hh slice lives in TENSOR MEMORY (A operand of tcgen05.mma, TS form): lane = gate row, 32-bit
+  // column j of the W region = (W[row][2j], W[row][2j+1]).  The MMA then reads only the small h tile
+  // from shared memory (the SS form re-reads the 128 KB slice every step: ~1000 smem-bound cycles).
+  uint8_t* h_smem = smem;                                         // 2 x hbuf_bytes    B operand, double buffered
   float* xch = reinterpret_cast<float*>(h_smem + 2 * hbuf_bytes); // [16 warps][32][XP]
   __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(xch + 16 * 32 * XP);   // [BC][32] new h of this slice
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(stage + BC * 32);
@@ -359,23 +363,30 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
       ptx::mbar_fence_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, BC < 32 ? 32 : BC);
+    ptx::tmem_alloc(tmem_slot, kTmemColsCluster);
     ptx::tmem_relinquish();
   }
-  if (!idle) {
-    const int chunks_per_row = H >> 3;
-    const uint4* src = reinterpret_cast<const uint4*>(sq.whh + static_cast<size_t>(slice) * 128 * H);
-    for (int e = tid; e < 128 * chunks_per_row; e += kLstmThreads) {
-      const int row = e / chunks_per_row;
-      const int cc = e - row * chunks_per_row;
-      *reinterpret_cast<uint4*>(w_smem + (cc >> 3) * 16384 + ptx::sw128_offset(row, cc & 7)) = __ldg(src + e);
-    }
-  }
-  ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (!idle) {
+    // warp (quarter, cg) fills rows 32*quarter.. of columns [cg*H/8, (cg+1)*H/8) of the W region
+    const int q4 = warp & 3, cgw = warp >> 2;
+    const int cols_per_warp = H >> 3;                               // 32-bit columns
+    const __nv_bfloat16* wrow = sq.whh + (static_cast<size_t>(slice) * 128 + q4 * 32 + lane) * H + cgw * (H >> 2);
+    const uint32_t tdst = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + kWCol0 + cgw * cols_per_warp;
+    for (int c = 0; c < cols_per_warp; c += 8) {
+      const uint4 lo = __ldg(reinterpret_cast<const uint4*>(wrow + 2 * c));
+      const uint4 hi = __ldg(reinterpret_cast<const uint4*>(wrow + 2 * c + 8));
+      const uint32_t regs[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      ptx::tmem_st_32x32b_x8(tdst + c, regs);
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
   ptx::cluster_sync_all();            // every peer's mbarriers are initialised before any remote arrive
 
   if (!idle) {
@@ -395,7 +406,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
     float* xw = xch + warp * 32 * XP;
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BC);
     const bool mma_leader = ptx::elect_one_sync();
-    const uint64_t w_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(w_smem));
+    const uint32_t w_tmem = tmem_base + kWCol0;    // A operand: 8 columns (16 bf16) per MMA
     const uint64_t h_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(h_smem));
     const uint16_t peer_mask = static_cast<uint16_t>(((1u << n_peers) - 1u) << peer0);
 
@@ -429,7 +440,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
             for (int kb = 0; kb < kblocks; ++kb) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                ptx::umma_bf16_ss(tmem_base, w_desc0 + static_cast<uint64_t>(kb * 1024 + 2 * k),
+                ptx::umma_bf16_ts(tmem_base, w_tmem + static_cast<uint32_t>(kb * 32 + k * 8),
                                   hd + static_cast<uint64_t>(kb * (BC * 8) + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             }
             ptx::umma_commit(mma_bar);
@@ -511,12 +522,12 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
   ptx::cluster_sync_all();             // no CTA exits while a peer's multicast may still target its smem
   if (warp == 0) {
     __syncwarp();
-    ptx::tmem_dealloc(tmem_base, BC < 32 ? 32 : BC);
+    ptx::tmem_dealloc(tmem_base, kTmemColsCluster);
   }
 }
 
 static size_t lstm_cluster_smem_bytes(int Hmax, int BC) {
-  return static_cast<size_t>(Hmax / 64) * 16384 + 2 * static_cast<size_t>(Hmax / 64) * BC * 128 +
+  return 2 * static_cast<size_t>(Hmax / 64) * BC * 128 +
          16 * 32 * (BC / 4 + 1) * 4 + static_cast<size_t>(BC) * 64 + 64 + 1024;
 }
 
@@ -585,7 +596,7 @@ static int lstm_cluster_plan(const amt_lstm_seq* seqs, int n_seq, int B, Cluster
   plan->ok = false;
   int CS = 0, Hmax = 0;
   for (int i = 0; i < n_seq; ++i) {
-    if (seqs[i].H % 64 != 0 || seqs[i].H < 64) return 0;
+    if (seqs[i].H % 64 != 0 || seqs[i].H < 64 || kWCol0 + seqs[i].H / 2 > kTmemColsCluster) return 0;
     CS = std::max(CS, seqs[i].H / 32);
     Hmax = std::max(Hmax, seqs[i].H);
   }
