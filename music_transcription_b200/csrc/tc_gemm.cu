@@ -23,12 +23,25 @@ struct GemmParams {
   int boxF_log2, boxT;
   int F, T, Bn;
   int tilesF, tilesT, n_tiles, num_tiles;
+  int m_tiles, group_n;   // rasterisation: n-tiles are swept in groups of group_n (weight slab stays in L2)
   const float* bias;
   void* out;
   long long ld_out;
   int Fout;
   int pool, relu;
 };
+
+// tile id -> (m tile, n tile).  n-tiles are visited in groups of group_n: inside a group the order is
+// m-major with n fastest, so the ~148 concurrently running tiles share group_n weight tiles (the
+// slab stays L2-resident while the activations stream past once per group).
+__device__ __forceinline__ int decode_tile(const GemmParams& p, int tile, int& m) {
+  const int per_group = p.m_tiles * p.group_n;
+  const int ng = tile / per_group;
+  const int rem = tile - ng * per_group;
+  const int gsize = min(p.group_n, p.n_tiles - ng * p.group_n);
+  m = rem / gsize;
+  return ng * p.group_n + (rem - m * gsize);
+}
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
@@ -93,41 +106,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // The whole warp runs the (warp-uniform) loop; only the issuing instructions are predicated on
     // one elected lane, so coordinates / addresses stay in uniform registers.
     const bool leader = ptx::elect_one_sync();
-    uint32_t it = 0;
+    // all per-k-block state is carried incrementally (no div/mod in the loop: the producer must stay
+    // well under the 128-cycle MMA time of a BN=64 k-block)
+    uint32_t s = 0, ph = 0;
+    uint8_t* a_dst = smem;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int m = tile / p.n_tiles;
-      const int n0 = (tile - m * p.n_tiles) * BN;
+      int m;
+      const int n0 = decode_tile(p, tile, m) * BN;
       const int f0 = (m % p.tilesF) * boxF;
       m /= p.tilesF;
       const int t0 = (m % p.tilesT) * p.boxT;
       const int b = m / p.tilesT;
-      for (int kb = 0; kb < kblocks; ++kb, ++it) {
-        const uint32_t s = it % Cfg::kStages;
-        const uint32_t ph = (it / Cfg::kStages) & 1;
+      int cb = 0, kt = 0;
+      int c1 = f0 - p.padF;                   // f coordinate of the current tap row
+      for (int kb = 0; kb < kblocks; ++kb) {
         ptx::mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* a_dst = smem + s * Cfg::kStageBytes;
-        uint8_t* b_dst = a_dst + kABytes;
-        int c0, c1, c2;
-        const CUtensorMap* am;
-        if (kb < p.kblocks0) {
-          const int tap = kb / p.cblk0;
-          const int kf = tap / p.ntapT;
-          c0 = (kb - tap * p.cblk0) * kBlockK;
-          c1 = f0 + kf - p.padF;
-          c2 = t0 + (tap - kf * p.ntapT) - p.padT;
-          am = &tmA0;
-        } else {
-          c0 = (kb - p.kblocks0) * kBlockK;
-          c1 = f0;
-          c2 = t0;
-          am = &tmA1;
-        }
+        const bool first = kb < p.kblocks0;
+        const CUtensorMap* am = first ? &tmA0 : &tmA1;
+        const int c0 = first ? cb * kBlockK : (kb - p.kblocks0) * kBlockK;
+        const int cf = first ? c1 : f0;
+        const int ct = first ? t0 + kt - p.padT : t0;
         if (leader) {
           ptx::mbar_expect_tx(&full[s], Cfg::kStageBytes);
-          ptx::tma_load_4d(a_dst, am, &full[s], c0, c1, c2, b);
-          ptx::tma_load_2d(b_dst, &tmB, &full[s], kb * kBlockK, n0);
+          ptx::tma_load_4d(a_dst, am, &full[s], c0, cf, ct, b);
+          ptx::tma_load_2d(a_dst + kABytes, &tmB, &full[s], kb * kBlockK, n0);
         }
         __syncwarp();
+        if (++cb == p.cblk0) {                // next tap: (kf, kt) row-major
+          cb = 0;
+          if (++kt == p.ntapT) {
+            kt = 0;
+            ++c1;
+          }
+        }
+        a_dst += Cfg::kStageBytes;
+        if (++s == Cfg::kStages) {
+          s = 0;
+          ph ^= 1;
+          a_dst = smem;
+        }
       }
     }
   } else if (warp == 1) {
@@ -135,20 +152,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool leader = ptx::elect_one_sync();
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, BN);
     const uint64_t desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smem));     // stage 0, A tile, k = 0
-    uint32_t it = 0, tl = 0;
+    uint32_t s = 0, ph = 0, tl = 0;
+    uint64_t a_desc = desc0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
       const uint32_t acc = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
       ptx::mbar_wait(&tempty[acc], aph ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < kblocks; ++kb, ++it) {
-        const uint32_t s = it % Cfg::kStages;
-        const uint32_t ph = (it / Cfg::kStages) & 1;
+      for (int kb = 0; kb < kblocks; ++kb) {
         ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
         // descriptors differ only in the 14-bit start-address field (units of 16 bytes)
-        const uint64_t a_desc = desc0 + static_cast<uint64_t>((s * Cfg::kStageBytes) >> 4);
         const uint64_t b_desc = a_desc + static_cast<uint64_t>(kABytes >> 4);
         if (leader) {
 #pragma unroll
@@ -157,6 +172,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           ptx::umma_commit(&empty[s]);   // frees the smem slot once these MMAs retire
         }
         __syncwarp();
+        a_desc += static_cast<uint64_t>(Cfg::kStageBytes >> 4);
+        if (++s == Cfg::kStages) {
+          s = 0;
+          ph ^= 1;
+          a_desc = desc0;
+        }
       }
       if (leader) ptx::umma_commit(&tfull[acc]);   // accumulator ready for the epilogue
       __syncwarp();
@@ -166,8 +187,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int q = warp & 3;              // TMEM lane quarter this warp may read
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
-      int m = tile / p.n_tiles;
-      const int n0 = (tile - m * p.n_tiles) * BN;
+      int m;
+      const int n0 = decode_tile(p, tile, m) * BN;
       const int f0 = (m % p.tilesF) * boxF;
       m /= p.tilesF;
       const int t0 = (m % p.tilesT) * p.boxT;
@@ -302,6 +323,8 @@ int run_conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   p.tilesF = ceil_div(d.F, d.boxF);
   p.tilesT = ceil_div(d.T, d.boxT);
   p.n_tiles = d.N / BN;
+  p.m_tiles = d.B * p.tilesF * p.tilesT;
+  p.group_n = p.n_tiles > 8 ? 8 : p.n_tiles;
   const long long nt = static_cast<long long>(d.B) * p.tilesF * p.tilesT * p.n_tiles;
   AMT_REQUIRE(nt < (1ll << 31), "conv/gemm: too many tiles");
   p.num_tiles = static_cast<int>(nt);
