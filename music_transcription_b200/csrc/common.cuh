@@ -125,6 +125,13 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split-phase cluster barrier (arrive now, wait later: independent work goes in between)
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // shared::cluster address of `local_smem_addr` (a shared::cta address) in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank) {
   uint32_t r;
@@ -138,6 +145,9 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint4 v) {
 }
 __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -309,6 +319,16 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c) {
 }
 
 // ---- misc ----
+// bar.sync on a named barrier: `count` threads (multiple of 32) of the CTA
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+// MUFU.TANH: one SFU op, max relative error 2^-11
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -351,14 +351,17 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
   float* xch = reinterpret_cast<float*>(h_smem + 2 * hbuf_bytes); // [16 warps][32][XP]
   __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(xch + 16 * 32 * XP);   // [BC][32] new h of this slice
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(stage + BC * 32);
-  uint64_t* hbar = mma_bar + 1;                                   // [2]: h tile buffer complete (n_peers arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hbar + 2);
+  uint64_t* hbar = mma_bar + 1;                                   // [2]: h tile buffer complete (multicast TMA complete_tx)
+  uint64_t* ready = hbar + 2;                                     // [2]: every slice of the sequence published h_t (issuer CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + 2);
 
   if (warp == 0) {
     if (lane == 0) {
       ptx::mbar_init(mma_bar, 1);
       ptx::mbar_init(&hbar[0], 1);
       ptx::mbar_init(&hbar[1], 1);
+      ptx::mbar_init(&ready[0], static_cast<uint32_t>(n_peers));
+      ptx::mbar_init(&ready[1], static_cast<uint32_t>(n_peers));
       ptx::prefetch_tmap(&tmH);
       ptx::mbar_fence_init();
     }
@@ -399,9 +402,10 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
     const int ul = r >> 2;                           // unit inside the slice
     const int unit = slice * 32 + ul;
     const int jlane = lane & 3;
-    const float act_k = gate == 2 ? 2.0f : 1.0f;
-    const float act_a = gate == 2 ? 2.0f : 1.0f;
-    const float act_c = gate == 2 ? -1.0f : 0.0f;
+    // activation as A*tanh(K*x)+C with ONE MUFU op: sigmoid(x) = 0.5*tanh(0.5x)+0.5 for i,f,o; tanh for g
+    const float act_k = gate == 2 ? 1.0f : 0.5f;
+    const float act_a = gate == 2 ? 1.0f : 0.5f;
+    const float act_c = gate == 2 ? 0.0f : 0.5f;
     const float* gx_row = sq.gx + slice * 128 + r;
     float* xw = xch + warp * 32 * XP;
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BC);
@@ -409,6 +413,9 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
     const uint32_t w_tmem = tmem_base + kWCol0;    // A operand: 8 columns (16 bf16) per MMA
     const uint64_t h_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(h_smem));
     const uint16_t peer_mask = static_cast<uint16_t>(((1u << n_peers) - 1u) << peer0);
+    const bool issuer = slice < kblocks;           // this CTA multicasts K block `slice` of h_t to every peer
+    // lane l < kblocks of warp 0 signals issuer l: shared::cluster address of ITS ready[] barriers
+    const uint32_t ready_remote = ptx::mapa(ptx::smem_u32(ready), static_cast<uint32_t>(peer0 + (lane < kblocks ? lane : 0)));
 
     float cstate[NC / 4];
 #pragma unroll
@@ -431,6 +438,25 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
       }
     }
 
+    // Layer outputs of step s are written during step s+1 (between MMA issue and MMA completion): their
+    // stores are then long retired when the next publish runs its gpu-scope membar, which otherwise has
+    // to drain them on the dependent chain.
+    const bool is_pub = tid < BC * 4;              // publishing thread: chunk pb, 8 units from pc*8 of the slice
+    const int pb = tid >> 2, pc = tid & 3;
+    uint4 pub_val = make_uint4(0u, 0u, 0u, 0u);
+    float hval[NC / 4];
+    auto store_outputs = [&](int tt) {
+      if (is_pub && sq.out_bf16 && pb < nvalid)
+        *reinterpret_cast<uint4*>(sq.out_bf16 + (static_cast<size_t>(b0 + pb) * p.T + tt) * sq.ld_out + slice * 32 + pc * 8) = pub_val;
+      if (sq.out_f32) {
+#pragma unroll
+        for (int m = 0; m < NC / 4; ++m) {
+          const int b = cg * NC + jlane + 4 * m;
+          if (b < nvalid) sq.out_f32[(static_cast<size_t>(b0 + b) * p.T + tt) * sq.ld_out32 + unit] = hval[m];
+        }
+      }
+    };
+
     for (int step = 0; step < p.T; ++step) {
       const int t = sq.reverse ? p.T - 1 - step : step;
       float gxv[NC];
@@ -449,6 +475,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
         const int buf = (step - 1) & 1;
         ptx::mbar_wait(&hbar[buf], ((step - 1) >> 1) & 1);     // all K blocks of h_{t-1} have landed (TMA complete_tx)
         TRACE_MARK(0);
+        store_outputs(sq.reverse ? t + 1 : t - 1);
         if (warp == 0) {
           ptx::tc_fence_after();
           if (mma_leader) {
@@ -480,7 +507,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         const float pre = __uint_as_float(v[j]) + gxv[j];
-        xw[lane * XP + j] = act_a * sigmoid_fast(act_k * pre) + act_c;
+        xw[lane * XP + j] = fmaf(act_a, ptx::tanh_approx(act_k * pre), act_c);
       }
       __syncwarp();
       const float* g4 = xw + (lane & ~3) * XP;
@@ -488,50 +515,48 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
       for (int m = 0; m < NC / 4; ++m) {
         const int j = jlane + 4 * m;
         const float gi = g4[j], gf = g4[XP + j], gg = g4[2 * XP + j], go = g4[3 * XP + j];
-        const float c = gf * cstate[m] + gi * gg;
+        const float c = fmaf(gf, cstate[m], gi * gg);
         cstate[m] = c;
-        const float h = go * (2.0f * sigmoid_fast(2.0f * c) - 1.0f);
-        const int b = cg * NC + j;
-        const __nv_bfloat16 hb = __float2bfloat16_rn(h);
-        stage[b * 32 + ul] = hb;
-        if (b < nvalid) {
-          const size_t row = static_cast<size_t>(b0 + b) * p.T + t;
-          if (sq.out_bf16) sq.out_bf16[row * sq.ld_out + unit] = hb;
-          if (sq.out_f32) sq.out_f32[row * sq.ld_out32 + unit] = h;
-        }
+        hval[m] = go * ptx::tanh_approx(c);
+        stage[(cg * NC + j) * 32 + ul] = __float2bfloat16_rn(hval[m]);
       }
       ptx::tc_fence_before();
       __syncthreads();                 // staging tile complete; all TMEM reads of this step retired
       TRACE_MARK(2);
 
-      // publish h_t: this slice's BC x 32 bf16 go to global (64-byte rows, L2 resident); after a cluster
-      // barrier the first `kblocks` slices each fetch one 64-unit K block of the assembled BC x H matrix
-      // with ONE multicast TMA that lands in buffer step&1 of every peer's swizzled B-operand tile.
-      {
+      // publish h_t (skipped after the last step: nobody consumes it).  This slice's BC x 32 bf16 go to
+      // global memory (64-byte rows, L2 resident); warp 0 then signals (release.cluster) the `kblocks`
+      // issuer CTAs of the sequence.  An issuer that has collected all n_peers signals fetches one 64-unit
+      // K block of the assembled BC x H matrix with ONE multicast TMA that lands in buffer step&1 of every
+      // peer's swizzled B-operand tile.  No cluster-wide barrier: a slice only ever waits for data.
+      if (is_pub) pub_val = *reinterpret_cast<const uint4*>(stage + pb * 32 + pc * 8);
+      if (step + 1 < p.T) {
         const int buf = step & 1;
         const int slot = (group * p.n_seq + q) * 2 + buf;
-        if (tid < BC * 4) {
-          const int b = tid >> 2, c = tid & 3;
-          const uint4 val = *reinterpret_cast<const uint4*>(stage + b * 32 + c * 8);
-          *reinterpret_cast<uint4*>(p.hglob + (static_cast<size_t>(slot) * BC + b) * p.Hmax + slice * 32 + c * 8) = val;
-          ptx::fence_proxy_async_all();      // generic-proxy global writes -> later async-proxy (TMA) reads
-        }
-        ptx::cluster_sync_all();             // release/acquire: every slice's rows are visible cluster-wide
-        TRACE_MARK(3);
-        if (tid == 0) {
+        if (is_pub) {
+          *reinterpret_cast<uint4*>(p.hglob + (static_cast<size_t>(slot) * BC + pb) * p.Hmax + slice * 32 + pc * 8) = pub_val;
+          ptx::named_bar_sync(1, BC * 4);
+          // ONE gpu-scope membar per signalling lane, after the barrier: it covers all BC*4 stores
+          // (cumulativity), so the rows are in L2 -- where the TMA reads them -- before the signal leaves.
+          if (warp == 0 && lane < kblocks) {
+            ptx::fence_proxy_async_all();
+            ptx::mbar_arrive_remote_relaxed(ready_remote + buf * 8);
+          }
+        } else if (warp == 15 && lane == 0) {
           ptx::mbar_expect_tx(&hbar[buf], static_cast<uint32_t>(hbuf_bytes));
-          if (slice < kblocks)
+          if (issuer) {
+            ptx::mbar_wait(&ready[buf], (step >> 1) & 1);
             ptx::tma_load_3d_multicast(h_smem + buf * hbuf_bytes + slice * (BC * 128), &tmH, &hbar[buf], slice * 64, 0, slot,
                                        peer_mask);
+          }
         }
       }
-      TRACE_MARK(4);
+      TRACE_MARK(3);
     }
+    store_outputs(sq.reverse ? 0 : p.T - 1);
     if (tracing)
       for (int i = 0; i < 6; ++i) p.trace[i] = tr[i];
 #undef TRACE_MARK
-  } else {
-    for (int step = 0; step < p.T; ++step) ptx::cluster_sync_all();   // padding CTA: keep the cluster barrier count
   }
 
   ptx::tc_fence_before();
@@ -738,8 +763,8 @@ int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, s
       AMT_CUDA(cudaStreamSynchronize(stream));
       AMT_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
       cudaFree(trace_dev);
-      fprintf(stderr, "[lstm cluster trace] n_seq=%d BC=%d CS=%d grid=%d T=%d cycles/step: tma-wait %.0f mma %.0f epilogue %.0f publish+cluster-barrier %.0f out-stores %.0f\n",
-              n_seq, cp.BC, cp.CS, grid, T, (double)h[0] / T, (double)h[1] / T, (double)h[2] / T, (double)h[3] / T, (double)h[4] / T);
+      fprintf(stderr, "[lstm cluster trace] n_seq=%d BC=%d CS=%d grid=%d T=%d cycles/step: h-wait %.0f out-stores+mma %.0f epilogue %.0f publish %.0f\n",
+              n_seq, cp.BC, cp.CS, grid, T, (double)h[0] / T, (double)h[1] / T, (double)h[2] / T, (double)h[3] / T);
     }
     return 0;
   }
