@@ -195,6 +195,15 @@ __device__ __forceinline__ void tma_load_3d_multicast(void* smem_dst, const CUte
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Bulk copy of `bytes` (multiple of 16) from this CTA's shared memory into a peer CTA's shared memory
+// (shared::cluster address from mapa); completes with complete_tx(bytes) on the peer's mbarrier.
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                  uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_cluster_addr),
+               "r"(src_cta_addr), "r"(bytes), "r"(bar_cluster_addr)
+               : "memory");
+}
 // generic-proxy writes (any state space) -> visible to later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
@@ -306,6 +315,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // SBO = 1024 B   [32,46)
   d |= static_cast<uint64_t>(1) << 46;                           // descriptor version (sm_100)
   d |= static_cast<uint64_t>(2) << 61;                           // SWIZZLE_128B
+  return d;
+}
+// K-major, 64-byte-swizzled operand: rows of 32 bf16 = 64 B, 8-row groups 512 B apart (tile base
+// 512-B aligned; + k_byte_offset < 64 for the K slice inside the atom).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(512 >> 4) << 32;                    // SBO = 512 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;                           // SWIZZLE_64B
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N.

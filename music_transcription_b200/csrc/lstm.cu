@@ -316,16 +316,16 @@ struct LstmClusterParams {
   unsigned char cta_seq[kMaxClusterCtas];     // sequence hosted by CTA w of a group (255 = idle padding)
   unsigned char cta_slice[kMaxClusterCtas];   // its slice of 32 hidden units
   unsigned char cta_peer0[kMaxClusterCtas];   // cluster rank of slice 0 of that sequence
-  __nv_bfloat16* hglob;  // [slots = groups*n_seq*2][BC][Hmax] bf16: h_t staging in global memory (L2 resident)
   int Hmax;
   long long* trace;
 };
 
 template <int BC>
 __global__ void __launch_bounds__(kLstmThreads, 1)
-lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterParams p) {
+lstm_cluster_kernel(const LstmClusterParams p) {
   constexpr int NC = BC / 4;
   constexpr int XP = NC + 1;
+  constexpr int kSliceBytes = BC * 64;             // one slice's h_t: BC rows x 32 units bf16, SWIZZLE_64B rows
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -341,28 +341,26 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
   const int peer0 = p.cta_peer0[within];
   const int H = sq.H;
   const int n_peers = sq.n_slices;
-  const int kblocks = H >> 6;
-  const int hbuf_bytes = kblocks * BC * 128;
+  const int hbuf_bytes = n_peers * kSliceBytes;
 
   // W_hh slice lives in TENSOR MEMORY (A operand of tcgen05.mma, TS form): lane = gate row, 32-bit
   // column j of the W region = (W[row][2j], W[row][2j+1]).  The MMA then reads only the small h tile
   // from shared memory (the SS form re-reads the 128 KB slice every step: ~1000 smem-bound cycles).
-  uint8_t* h_smem = smem;                                         // 2 x hbuf_bytes    B operand, double buffered
-  float* xch = reinterpret_cast<float*>(h_smem + 2 * hbuf_bytes); // [16 warps][32][XP]
-  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(xch + 16 * 32 * XP);   // [BC][32] new h of this slice
-  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(stage + BC * 32);
-  uint64_t* hbar = mma_bar + 1;                                   // [2]: h tile buffer complete (multicast TMA complete_tx)
-  uint64_t* ready = hbar + 2;                                     // [2]: every slice of the sequence published h_t (issuer CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + 2);
+  // B operand: h_{t-1} as n_peers blocks of [BC rows][32 units] (64-byte rows, SWIZZLE_64B), block s
+  // written by slice s -- each block is ONE contiguous 2 KB region, so a peer delivers it with a single
+  // bulk DSMEM copy.
+  uint8_t* h_smem = smem;                                         // 2 x hbuf_bytes, double buffered
+  uint8_t* stage = h_smem + 2 * hbuf_bytes;                       // 2 x kSliceBytes: this slice's new h (pre-swizzled)
+  float* xch = reinterpret_cast<float*>(stage + 2 * kSliceBytes); // [16 warps][32][XP]
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(xch + 16 * 32 * XP);
+  uint64_t* hbar = mma_bar + 1;                                   // [2]: h tile buffer complete (n_peers x kSliceBytes of complete_tx)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hbar + 2);
 
   if (warp == 0) {
     if (lane == 0) {
       ptx::mbar_init(mma_bar, 1);
       ptx::mbar_init(&hbar[0], 1);
       ptx::mbar_init(&hbar[1], 1);
-      ptx::mbar_init(&ready[0], static_cast<uint32_t>(n_peers));
-      ptx::mbar_init(&ready[1], static_cast<uint32_t>(n_peers));
-      ptx::prefetch_tmap(&tmH);
       ptx::mbar_fence_init();
     }
     __syncwarp();
@@ -411,11 +409,14 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BC);
     const bool mma_leader = ptx::elect_one_sync();
     const uint32_t w_tmem = tmem_base + kWCol0;    // A operand: 8 columns (16 bf16) per MMA
-    const uint64_t h_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(h_smem));
-    const uint16_t peer_mask = static_cast<uint16_t>(((1u << n_peers) - 1u) << peer0);
-    const bool issuer = slice < kblocks;           // this CTA multicasts K block `slice` of h_t to every peer
-    // lane l < kblocks of warp 0 signals issuer l: shared::cluster address of ITS ready[] barriers
-    const uint32_t ready_remote = ptx::mapa(ptx::smem_u32(ready), static_cast<uint32_t>(peer0 + (lane < kblocks ? lane : 0)));
+    const uint64_t h_desc0 = ptx::umma_desc_sw64(ptx::smem_u32(h_smem));
+    // lane l < n_peers of warp 15 delivers this slice's block to peer l: shared::cluster addresses of the
+    // peer's block `slice` (buffer 0) and of its hbar[0]
+    const uint32_t peer_rank = static_cast<uint32_t>(peer0 + (lane < n_peers ? lane : 0));
+    const uint32_t peer_dst = ptx::mapa(ptx::smem_u32(h_smem + slice * kSliceBytes), peer_rank);
+    const uint32_t peer_bar = ptx::mapa(ptx::smem_u32(hbar), peer_rank);
+    // this thread's cell (unit ul, chunk b) in the pre-swizzled staging block: row b, 16-byte chunk ul/8
+    auto stage_off = [&](int b) { return b * 64 + ((((ul >> 3) ^ (b >> 1)) & 3) << 4) + (ul & 7) * 2; };
 
     float cstate[NC / 4];
 #pragma unroll
@@ -480,11 +481,11 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
           ptx::tc_fence_after();
           if (mma_leader) {
             const uint64_t hd = h_desc0 + static_cast<uint64_t>((buf * hbuf_bytes) >> 4);
-            for (int kb = 0; kb < kblocks; ++kb) {
+            for (int sb = 0; sb < n_peers; ++sb) {           // one 32-unit block per slice, two K=16 MMAs each
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                ptx::umma_bf16_ts(tmem_base, w_tmem + static_cast<uint32_t>(kb * 32 + k * 8),
-                                  hd + static_cast<uint64_t>(kb * (BC * 8) + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 2; ++k)
+                ptx::umma_bf16_ts(tmem_base, w_tmem + static_cast<uint32_t>(sb * 16 + k * 8),
+                                  hd + static_cast<uint64_t>(sb * (kSliceBytes >> 4) + 2 * k), idesc, (sb | k) != 0 ? 1u : 0u);
             }
             ptx::umma_commit(mma_bar);
           }
@@ -496,6 +497,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
         TRACE_MARK(1);
       }
 
+      uint8_t* stage_t = stage + (step & 1) * kSliceBytes;
       uint32_t v[NC];
       if (step > 0) {
         ptx::tmem_ld_cols<NC>(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + cg * NC, v);
@@ -518,38 +520,27 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
         const float c = fmaf(gf, cstate[m], gi * gg);
         cstate[m] = c;
         hval[m] = go * ptx::tanh_approx(c);
-        stage[(cg * NC + j) * 32 + ul] = __float2bfloat16_rn(hval[m]);
+        *reinterpret_cast<__nv_bfloat16*>(stage_t + stage_off(cg * NC + j)) = __float2bfloat16_rn(hval[m]);
       }
+      ptx::fence_proxy_async_smem();   // generic-proxy staging writes -> async-proxy (bulk copy) reads
       ptx::tc_fence_before();
-      __syncthreads();                 // staging tile complete; all TMEM reads of this step retired
+      __syncthreads();                 // staging block complete; all TMEM reads of this step retired
       TRACE_MARK(2);
 
-      // publish h_t (skipped after the last step: nobody consumes it).  This slice's BC x 32 bf16 go to
-      // global memory (64-byte rows, L2 resident); warp 0 then signals (release.cluster) the `kblocks`
-      // issuer CTAs of the sequence.  An issuer that has collected all n_peers signals fetches one 64-unit
-      // K block of the assembled BC x H matrix with ONE multicast TMA that lands in buffer step&1 of every
-      // peer's swizzled B-operand tile.  No cluster-wide barrier: a slice only ever waits for data.
-      if (is_pub) pub_val = *reinterpret_cast<const uint4*>(stage + pb * 32 + pc * 8);
-      if (step + 1 < p.T) {
+      // publish h_t (skipped after the last step: nobody consumes it): 16 lanes each push this slice's
+      // 2 KB block with ONE bulk DSMEM copy into block `slice` of buffer step&1 of a peer's B-operand tile;
+      // the copy completes (complete_tx) on that peer's hbar.  No L2 round trip, no membar, no barrier:
+      // a slice only ever waits for data.  Buffer step&1 of a peer was last read by its MMAs of step-1, and
+      // the peer published h_{step-1} -- which this CTA's step needed -- only after those MMAs retired.
+      if (is_pub) {
+        const int chunk = pc ^ ((pb >> 1) & 3);
+        pub_val = *reinterpret_cast<const uint4*>(stage_t + pb * 64 + chunk * 16);
+      }
+      if (step + 1 < p.T && warp == 15) {
         const int buf = step & 1;
-        const int slot = (group * p.n_seq + q) * 2 + buf;
-        if (is_pub) {
-          *reinterpret_cast<uint4*>(p.hglob + (static_cast<size_t>(slot) * BC + pb) * p.Hmax + slice * 32 + pc * 8) = pub_val;
-          ptx::named_bar_sync(1, BC * 4);
-          // ONE gpu-scope membar per signalling lane, after the barrier: it covers all BC*4 stores
-          // (cumulativity), so the rows are in L2 -- where the TMA reads them -- before the signal leaves.
-          if (warp == 0 && lane < kblocks) {
-            ptx::fence_proxy_async_all();
-            ptx::mbar_arrive_remote_relaxed(ready_remote + buf * 8);
-          }
-        } else if (warp == 15 && lane == 0) {
-          ptx::mbar_expect_tx(&hbar[buf], static_cast<uint32_t>(hbuf_bytes));
-          if (issuer) {
-            ptx::mbar_wait(&ready[buf], (step >> 1) & 1);
-            ptx::tma_load_3d_multicast(h_smem + buf * hbuf_bytes + slice * (BC * 128), &tmH, &hbar[buf], slice * 64, 0, slot,
-                                       peer_mask);
-          }
-        }
+        if (lane == 0) ptx::mbar_expect_tx(&hbar[buf], static_cast<uint32_t>(hbuf_bytes));
+        if (lane < n_peers)
+          ptx::bulk_copy_to_peer(peer_dst + buf * hbuf_bytes, ptx::smem_u32(stage_t), kSliceBytes, peer_bar + buf * 8);
       }
       TRACE_MARK(3);
     }
@@ -568,8 +559,8 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmH, const LstmClusterPa
 }
 
 static size_t lstm_cluster_smem_bytes(int Hmax, int BC) {
-  return 2 * static_cast<size_t>(Hmax / 64) * BC * 128 +
-         16 * 32 * (BC / 4 + 1) * 4 + static_cast<size_t>(BC) * 64 + 64 + 1024;
+  return 2 * static_cast<size_t>(Hmax / 32) * BC * 64 + 2 * static_cast<size_t>(BC) * 64 +
+         16 * 32 * (BC / 4 + 1) * 4 + 64 + 1024;
 }
 
 struct ClusterPlan {
@@ -621,12 +612,12 @@ static int lstm_cluster_max_active(int CS, size_t smem, int* out) {
 }
 
 template <int BC>
-static int lstm_cluster_launch(const CUtensorMap& tm, const LstmClusterParams& p, int grid, int CS, size_t smem,
+static int lstm_cluster_launch(const LstmClusterParams& p, int grid, int CS, size_t smem,
                                cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   AMT_TRY(lstm_cluster_config<BC>(&cfg, attr, grid, CS, smem, stream));
-  AMT_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<BC>, tm, p));
+  AMT_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<BC>, p));
   count_launch();
   return 0;
 }
@@ -743,21 +734,12 @@ int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, s
     const int n_groups = ceil_div(B, cp.BC);
     const int grid = n_groups * cp.ctas_per_group;
     const size_t smem = lstm_cluster_smem_bytes(cp.Hmax, cp.BC);
-    const size_t slots = static_cast<size_t>(n_groups) * n_seq * 2;
-    const size_t need = slots * cp.BC * cp.Hmax * 2;
-    if (scratch_bytes < need) return set_error(AMT_ERR_WORKSPACE, "lstm: scratch %zu < %zu bytes", scratch_bytes, need);
-    p.hglob = static_cast<__nv_bfloat16*>(scratch);
     p.Hmax = cp.Hmax;
-    CUtensorMap tm;
-    {
-      uint64_t dims[3] = {(uint64_t)cp.Hmax, (uint64_t)cp.BC, (uint64_t)slots};
-      uint64_t str[2] = {(uint64_t)cp.Hmax * 2, (uint64_t)cp.BC * cp.Hmax * 2};
-      uint32_t box[3] = {64, (uint32_t)cp.BC, 1};
-      AMT_TRY(encode_tmap_bf16(&tm, scratch, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
-    }
-    if (cp.BC == 16) AMT_TRY(lstm_cluster_launch<16>(tm, p, grid, cp.CS, smem, stream));
-    else if (cp.BC == 32) AMT_TRY(lstm_cluster_launch<32>(tm, p, grid, cp.CS, smem, stream));
-    else AMT_TRY(lstm_cluster_launch<64>(tm, p, grid, cp.CS, smem, stream));
+    (void)scratch;
+    (void)scratch_bytes;          // the cluster path exchanges h through distributed shared memory only
+    if (cp.BC == 16) AMT_TRY(lstm_cluster_launch<16>(p, grid, cp.CS, smem, stream));
+    else if (cp.BC == 32) AMT_TRY(lstm_cluster_launch<32>(p, grid, cp.CS, smem, stream));
+    else AMT_TRY(lstm_cluster_launch<64>(p, grid, cp.CS, smem, stream));
     if (trace_on) {   // debug only: host sync + print
       long long h[6];
       AMT_CUDA(cudaStreamSynchronize(stream));
