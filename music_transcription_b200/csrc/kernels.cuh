@@ -18,6 +18,10 @@ struct ConvGemmDesc {
 };
 
 int run_conv_gemm(const ConvGemmDesc& d, cudaStream_t stream);
+// halo-tile implicit-GEMM convolution (conv_halo.cu): X [B][T][F][C], optional 1x1 skip source X2 [B][T][F][C2],
+// W [N][kf*kt*C + C2] (K index = (kf, kt, c)), out [B][T][F or F/2][N] bf16
+int run_conv_halo(const void* X, int C, const void* X2, int C2, int B, int T, int F, const void* W, const float* bias,
+                  int N, int kf, int kt, void* out, int relu, int pool, cudaStream_t stream);
 int run_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, long long ldc, int relu,
              int out_f32, cudaStream_t stream);
 int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, size_t scratch_bytes, cudaStream_t stream);

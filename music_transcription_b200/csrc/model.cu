@@ -2,6 +2,7 @@
 // (reference models/cnn_rnn_model.py:57-74 and :262-349) as a fixed sequence of
 // kernel launches on the caller's stream.  All intermediate tensors live in the
 // caller-provided workspace; weights are the packed tensors registered by name.
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -200,6 +201,8 @@ static const float* F_(const amt_model& m, const std::string& n) { return static
 
 static int conv(const amt_model&, const void* X, int C, const void* X2, int C2, int B, int T, int F, const void* W,
                 const float* bias, int N, int kf, int kt, void* out, int pool, cudaStream_t s) {
+  static const bool taps = getenv("AMT_CONV_TAPS") != nullptr;     // bring-up switch: tap-by-tap TMA boxes
+  if (!taps) return run_conv_halo(X, C, X2, C2, B, T, F, W, bias, N, kf, kt, out, 1, pool, s);
   ConvGemmDesc d{};
   d.X = X; d.C = C; d.X2 = X2; d.C2 = C2;
   d.B = B; d.T = T; d.F = F;

@@ -13,6 +13,8 @@
 // warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU/freq-max-pool -> global).  The
 // accumulator is double buffered in TMEM so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  Tile = 128 (M) x BN (N), BLOCK_K = 64 bf16 = one 128-B swizzle atom.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace amt {
@@ -370,6 +372,10 @@ int amt_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int 
 
 int amt_conv_bf16(const void* X, const void* X2, const void* W, const float* bias, void* Y, int B, int T, int F,
                   int Cin, int Cin2, int Cout, int kf, int kt, int relu, int pool, amt_stream_t stream) {
+  static const bool taps = getenv("AMT_CONV_TAPS") != nullptr;     // bring-up switch: tap-by-tap TMA boxes
+  if (!taps)
+    return amt::run_conv_halo(X, Cin, X2, Cin2, B, T, F, W, bias, Cout, kf, kt, Y, relu, pool,
+                              static_cast<cudaStream_t>(stream));
   amt::ConvGemmDesc d{};
   d.X = X; d.C = Cin; d.X2 = X2; d.C2 = Cin2;
   d.B = B; d.T = T; d.F = F;

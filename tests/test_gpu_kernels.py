@@ -83,6 +83,10 @@ def _pack_w(w):     # [Co,Ci,kf,kt] -> [Co, kf*kt*Ci]
     (1, 50, 9, 128, 256, 7, 3, 1, 0),
     (2, 21, 40, 128, 128, 3, 3, 0, 64),
     (1, 938, 80, 64, 64, 3, 3, 1, 64),
+    (2, 33, 24, 32, 64, 3, 3, 0, 0),          # 32-channel input (stem output): 64-byte rows, SWIZZLE_64B
+    (1, 70, 40, 64, 64, 3, 3, 1, 32),         # 64-channel main + 32-channel skip source
+    (1, 19, 160, 32, 64, 3, 3, 1, 0),
+    (1, 40, 80, 128, 256, 7, 3, 1, 0),
 ])
 def test_conv_implicit_gemm_matches_conv2d(B, T, Fq, Ci, Co, kf, kt, pool, skip):
     g = torch.Generator().manual_seed(B * 1000 + T + Fq + Ci + Co)

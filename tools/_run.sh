@@ -1,10 +1,12 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k lstm -x --timeout 120 2>&1 | tail -5
-AMT_LSTM_TRACE=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/trace.json 2> gpurun_out/trace.err; grep "trace" gpurun_out/trace.err | head -3
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_a.json 2> gpurun_out/bench_a.err; tail -c 300 gpurun_out/bench_a.err
+timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k conv --timeout 120 2>&1 | tail -15
+for v in halo; do
+  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err; tail -c 300 gpurun_out/bench_$v.err
+done
 python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/bench_a.json").read().strip().splitlines()[-1])
-print(d["value"], d["ms_per_step"], d["e2e"]["value"])
-print([(s["stage"], s["ms_per_launch"]) for s in d["stages"]][:14])
+for v in ("halo",):
+    d=json.loads(open(f"gpurun_out/bench_{v}.json").read().strip().splitlines()[-1])
+    print(v, d["value"], d["ms_per_step"], d["e2e"]["value"])
+    print([(s["stage"], s["ms_per_launch"], s.get("tflops")) for s in d["stages"] if s["stage"].startswith(("res","freq","conv"))])
 PY
