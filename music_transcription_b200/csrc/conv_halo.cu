@@ -42,6 +42,7 @@ struct ConvHaloParams {
   int kmain;                    // weight columns of the main conv = kf*kt*C
   const float* bias;
   int pool, relu;
+  int resident;                 // all weight blocks of a tile fit the B ring: loaded once, never released
 };
 
 template <int KC, int BN>
@@ -51,10 +52,10 @@ struct ConvHaloCfg {
   static constexpr int kBBytes = BN * kRowBytes;
   static constexpr int kAStages = BN == 256 ? 2 : 3;
   static constexpr int kOutBytes = 2 * 128 * 128;                      // two staged [128 rows x 64 ch] output chunks
-  static constexpr int kBudget = 225 * 1024 - kAStages * kABytes - kOutBytes - BN * 4 - 1024 - 256;
+  static constexpr int kBudget = 225 * 1024 - kAStages * kABytes - kOutBytes - BN * 4 - 1024 - 512;
   static constexpr int kBStagesRaw = kBudget / kBBytes;
-  static constexpr int kBStages = kBStagesRaw > 8 ? 8 : kBStagesRaw;
-  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + kOutBytes + BN * 4 + 1024 + 256;
+  static constexpr int kBStages = kBStagesRaw > 16 ? 16 : kBStagesRaw;   // 16 covers every resident case (<= 10 blocks)
+  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + kOutBytes + BN * 4 + 1024 + 512;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(kBStages >= 3, "weight ring too small");
 };
@@ -74,7 +75,7 @@ constexpr int kConvThreads = 352;
 constexpr int kEpiWarp0 = 3;        // first epilogue warp
 constexpr int kEpiThreads = 256;
 
-template <int KC, int BN>
+template <int KC, int BN, int KF>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -132,7 +133,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int taps = p.kf * p.kt;
+  constexpr int taps = KF * 3;
 
   if (warp == 0) {
     // -------------------- activation producer: one halo box per channel block --------------------
@@ -168,6 +169,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const bool leader = ptx::elect_one_sync();
     uint32_t s = 0, ph = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      if (p.resident && tile != static_cast<int>(blockIdx.x)) break;      // weights stay in smem after the first tile
       for (int e = 0; e < p.cblks; ++e) {
         int col = e * KC;                       // weight column of (tap 0, block e); taps are cblks*KC apart
         for (int tap = 0; tap < taps; ++tap) {
@@ -199,8 +201,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 2) {
     // -------------------- MMA issuer --------------------
+    // The loop bodies are issue-bound for the small-N layers (a tap is only KC/16 MMAs of 32-64 tensor
+    // cycles), so all per-tap state is carried incrementally and the filter loop is unrolled (kt == 3,
+    // KF compile-time); with resident weights a tile is one straight-line burst of MMAs.
     const bool leader = ptx::elect_one_sync();
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
+    constexpr uint64_t kRow16 = Cfg::kRowBytes >> 4;            // one halo row, in descriptor address units
+    constexpr uint64_t kBStage16 = Cfg::kBBytes >> 4;
     const uint32_t a_addr0 = ptx::smem_u32(a_smem), b_addr0 = ptx::smem_u32(b_smem);
     // halo tile: frame rows are kHaloF rows apart; plain (skip) tile and weights: 8-row groups contiguous
     const uint64_t a_halo0 = conv_desc(a_addr0, kHaloF * Cfg::kRowBytes, Cfg::kRowBytes);
@@ -209,64 +216,122 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint64_t a_skip0 = conv_desc(a_addr0, 8 * row2, row2);
     const uint64_t b_skip0 = conv_desc(b_addr0, 8 * row2, row2);
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tl = 0;
+    uint64_t a_stage = 0, b_stage = 0;                          // descriptor offsets of A stage sa / B stage sb
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
       const uint32_t acc = tl & 1;
       ptx::mbar_wait(&tempty[acc], ((tl >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
       uint32_t first = 0;                       // 0 until the tile's first MMA was issued
-      for (int e = 0; e < p.cblks; ++e) {
-        ptx::mbar_wait(&afull[sa], pa);
-        const uint64_t a_tile = a_halo0 + static_cast<uint64_t>((sa * Cfg::kABytes) >> 4);
-        int kfi = 0, kti = 0;
-        for (int tap = 0; tap < taps; ++tap) {
-          ptx::mbar_wait(&bfull[sb], pb);
+      if (p.resident) {
+        if (tl == 0)                            // weights arrive once; they are never released
+          for (int i = 0; i < p.cblks * KF * 3 + p.cblks2; ++i) ptx::mbar_wait(&bfull[i], 0);
+        uint64_t b_desc = b_main0;
+        for (int e = 0; e < p.cblks; ++e) {
+          ptx::mbar_wait(&afull[sa], pa);
           ptx::tc_fence_after();
-          const uint64_t a_desc = a_tile + static_cast<uint64_t>(((kti * kHaloF + kfi) * Cfg::kRowBytes) >> 4);
-          const uint64_t b_desc = b_main0 + static_cast<uint64_t>((sb * Cfg::kBBytes) >> 4);
           if (leader) {
+            const uint64_t a_tile = a_halo0 + a_stage;
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, first | k);
-            ptx::umma_commit(&bempty[sb]);
+            for (int kfi = 0; kfi < KF; ++kfi)
+#pragma unroll
+              for (int kti = 0; kti < 3; ++kti)
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k)
+                  ptx::umma_bf16_ss(d_tmem, a_tile + (kti * kHaloF + kfi) * kRow16 + 2 * k,
+                                    b_desc + (kfi * 3 + kti) * kBStage16 + 2 * k, idesc, first | kfi | kti | k);
+            ptx::umma_commit(&aempty[sa]);
           }
           __syncwarp();
           first = 1;
-          if (++kti == p.kt) {                  // weight K order is (kf, kt, c): kt fastest
-            kti = 0;
-            ++kfi;
+          b_desc += KF * 3 * kBStage16;
+          a_stage += Cfg::kABytes >> 4;
+          if (++sa == Cfg::kAStages) {
+            sa = 0;
+            pa ^= 1;
+            a_stage = 0;
           }
+        }
+        const uint64_t b_skip = b_skip0 + (b_desc - b_main0);
+        for (int e = 0; e < p.cblks2; ++e) {
+          ptx::mbar_wait(&afull[sa], pa);
+          ptx::tc_fence_after();
+          if (leader) {
+            for (int k = 0; k < p.kc2 / 16; ++k)
+              ptx::umma_bf16_ss(d_tmem, a_skip0 + a_stage + 2 * k, b_skip + e * kBStage16 + 2 * k, idesc, first | k);
+            ptx::umma_commit(&aempty[sa]);
+          }
+          __syncwarp();
+          first = 1;
+          a_stage += Cfg::kABytes >> 4;
+          if (++sa == Cfg::kAStages) {
+            sa = 0;
+            pa ^= 1;
+            a_stage = 0;
+          }
+        }
+      } else {
+        for (int e = 0; e < p.cblks; ++e) {
+          ptx::mbar_wait(&afull[sa], pa);
+          uint64_t a_row = a_halo0 + a_stage;   // tap (kf = 0, kt = 0)
+#pragma unroll 1
+          for (int kfi = 0; kfi < KF; ++kfi) {
+#pragma unroll
+            for (int kti = 0; kti < 3; ++kti) {   // weight K order is (kf, kt, c): kt fastest
+              ptx::mbar_wait(&bfull[sb], pb);
+              ptx::tc_fence_after();
+              if (leader) {
+                const uint64_t a_desc = a_row + kti * kHaloF * kRow16;
+                const uint64_t b_desc = b_main0 + b_stage;
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k)
+                  ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, first | kti | k);
+                ptx::umma_commit(&bempty[sb]);
+              }
+              __syncwarp();
+              b_stage += kBStage16;
+              if (++sb == Cfg::kBStages) {
+                sb = 0;
+                pb ^= 1;
+                b_stage = 0;
+              }
+            }
+            first = 1;
+            a_row += kRow16;
+          }
+          if (leader) ptx::umma_commit(&aempty[sa]);
+          __syncwarp();
+          a_stage += Cfg::kABytes >> 4;
+          if (++sa == Cfg::kAStages) {
+            sa = 0;
+            pa ^= 1;
+            a_stage = 0;
+          }
+        }
+        for (int e = 0; e < p.cblks2; ++e) {    // residual 1x1 skip conv: plain tile, centre tap only
+          ptx::mbar_wait(&afull[sa], pa);
+          ptx::mbar_wait(&bfull[sb], pb);
+          ptx::tc_fence_after();
+          if (leader) {
+            for (int k = 0; k < p.kc2 / 16; ++k)
+              ptx::umma_bf16_ss(d_tmem, a_skip0 + a_stage + 2 * k, b_skip0 + b_stage + 2 * k, idesc, first | k);
+            ptx::umma_commit(&bempty[sb]);
+            ptx::umma_commit(&aempty[sa]);
+          }
+          __syncwarp();
+          first = 1;
+          b_stage += kBStage16;
           if (++sb == Cfg::kBStages) {
             sb = 0;
             pb ^= 1;
+            b_stage = 0;
           }
-        }
-        if (leader) ptx::umma_commit(&aempty[sa]);
-        __syncwarp();
-        if (++sa == Cfg::kAStages) {
-          sa = 0;
-          pa ^= 1;
-        }
-      }
-      for (int e = 0; e < p.cblks2; ++e) {      // residual 1x1 skip conv: plain tile, centre tap only
-        ptx::mbar_wait(&afull[sa], pa);
-        ptx::mbar_wait(&bfull[sb], pb);
-        ptx::tc_fence_after();
-        const uint64_t a_desc = a_skip0 + static_cast<uint64_t>((sa * Cfg::kABytes) >> 4);
-        const uint64_t b_desc = b_skip0 + static_cast<uint64_t>((sb * Cfg::kBBytes) >> 4);
-        if (leader) {
-          for (int k = 0; k < p.kc2 / 16; ++k) ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, first | k);
-          ptx::umma_commit(&bempty[sb]);
-          ptx::umma_commit(&aempty[sa]);
-        }
-        __syncwarp();
-        first = 1;
-        if (++sb == Cfg::kBStages) {
-          sb = 0;
-          pb ^= 1;
-        }
-        if (++sa == Cfg::kAStages) {
-          sa = 0;
-          pa ^= 1;
+          a_stage += Cfg::kABytes >> 4;
+          if (++sa == Cfg::kAStages) {
+            sa = 0;
+            pa ^= 1;
+            a_stage = 0;
+          }
         }
       }
       if (leader) ptx::umma_commit(&tfull[acc]);
@@ -353,17 +418,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 }
 
-template <int KC, int BN>
+template <int KC, int BN, int KF>
 static int launch_conv_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
                             const CUtensorMap& o, const ConvHaloParams& p, cudaStream_t stream) {
   using Cfg = ConvHaloCfg<KC, BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    AMT_CUDA(cudaFuncSetAttribute(conv_halo_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    AMT_CUDA(cudaFuncSetAttribute(conv_halo_kernel<KC, BN, KF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv_halo_kernel<KC, BN><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, o, p);
+  ConvHaloParams q = p;
+  q.resident = (p.cblks * KF * 3 + p.cblks2 <= Cfg::kBStages) ? 1 : 0;
+  conv_halo_kernel<KC, BN, KF><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, o, q);
   AMT_CHECK_LAUNCH();
   return 0;
 }
@@ -377,8 +444,8 @@ int run_conv_halo(const void* X, int C, const void* X2, int C2, int B, int T, in
   AMT_REQUIRE(C == 32 || C % 64 == 0, "conv: Cin (%d) must be 32 or a multiple of 64", C);
   AMT_REQUIRE(X2 == nullptr || C2 == 32 || C2 % 64 == 0, "conv: skip Cin (%d) must be 32 or a multiple of 64", C2);
   AMT_REQUIRE(N == 64 || N == 128 || N == 256, "conv: Cout (%d) must be 64, 128 or 256", N);
-  AMT_REQUIRE((kf & 1) && (kt & 1) && kf <= kHaloF - kTileF + 1 && kt <= kHaloT - kTileT + 1,
-              "conv: filter %dx%d unsupported (odd, <= %dx%d)", kf, kt, kHaloF - kTileF + 1, kHaloT - kTileT + 1);
+  AMT_REQUIRE((kf == 3 || kf == 7) && kt == 3, "conv: filter %dx%d unsupported (3x3 and 7x3 are built)", kf, kt);
+  AMT_REQUIRE(kf == 3 || C % 64 == 0, "conv: the 7x3 filter needs Cin %% 64 == 0");
   const int KC = C == 32 ? 32 : 64;
   const int c2 = X2 ? C2 : 0;
   const int kc2 = c2 == 0 ? KC : (c2 == 32 ? 32 : 64);
@@ -436,15 +503,21 @@ int run_conv_halo(const void* X, int C, const void* X2, int C2, int B, int T, in
   p.bias = bias;
   p.pool = pool;
   p.relu = relu;
+  p.resident = 0;
 
-  if (KC == 32) {
-    if (N == 64) return launch_conv_halo<32, 64>(a0, a1, b0, b1, om, p, stream);
-    if (N == 128) return launch_conv_halo<32, 128>(a0, a1, b0, b1, om, p, stream);
-    return launch_conv_halo<32, 256>(a0, a1, b0, b1, om, p, stream);
+  if (kf == 7) {
+    if (N == 64) return launch_conv_halo<64, 64, 7>(a0, a1, b0, b1, om, p, stream);
+    if (N == 128) return launch_conv_halo<64, 128, 7>(a0, a1, b0, b1, om, p, stream);
+    return launch_conv_halo<64, 256, 7>(a0, a1, b0, b1, om, p, stream);
   }
-  if (N == 64) return launch_conv_halo<64, 64>(a0, a1, b0, b1, om, p, stream);
-  if (N == 128) return launch_conv_halo<64, 128>(a0, a1, b0, b1, om, p, stream);
-  return launch_conv_halo<64, 256>(a0, a1, b0, b1, om, p, stream);
+  if (KC == 32) {
+    if (N == 64) return launch_conv_halo<32, 64, 3>(a0, a1, b0, b1, om, p, stream);
+    if (N == 128) return launch_conv_halo<32, 128, 3>(a0, a1, b0, b1, om, p, stream);
+    return launch_conv_halo<32, 256, 3>(a0, a1, b0, b1, om, p, stream);
+  }
+  if (N == 64) return launch_conv_halo<64, 64, 3>(a0, a1, b0, b1, om, p, stream);
+  if (N == 128) return launch_conv_halo<64, 128, 3>(a0, a1, b0, b1, om, p, stream);
+  return launch_conv_halo<64, 256, 3>(a0, a1, b0, b1, om, p, stream);
 }
 
 }  // namespace amt

@@ -88,12 +88,12 @@ static std::vector<Expect> expected_tensors(const amt_model& m) {
   e.push_back({"conv1.w", f32(32 * 9)});
   e.push_back({"conv1.b", f32(32)});
   if (c.kind == AMT_MODEL_CNN_RNN) {
-    e.push_back({"c2.w", bf(64ull * 9 * 64)});
+    e.push_back({"c2.w", bf(64ull * 9 * 32)});
     e.push_back({"c2.b", f32(64)});
   } else {
-    e.push_back({"res1.c1.w", bf(64ull * 9 * 64)});
+    e.push_back({"res1.c1.w", bf(64ull * 9 * 32)});
     e.push_back({"res1.c1.b", f32(64)});
-    e.push_back({"res1.c2.w", bf(64ull * (9 * 64 + 64))});
+    e.push_back({"res1.c2.w", bf(64ull * (9 * 64 + 32))});
     e.push_back({"res1.c2.b", f32(64)});
     e.push_back({"res2.c1.w", bf(128ull * 9 * 64)});
     e.push_back({"res2.c1.b", f32(128)});
@@ -158,7 +158,7 @@ static size_t carve(const amt_model& m, int B, int T, void* ws, Buffers* b) {
   Workspace w(ws);
   const size_t BT = static_cast<size_t>(B) * T;
   const bool large = m.cfg.kind == AMT_MODEL_CNN_RNN_LARGE;
-  b->act1 = w.take(BT * m.F1 * 64 * 2);
+  b->act1 = w.take(BT * m.F1 * 32 * 2);
   if (large) {
     b->h1 = w.take(BT * m.F1 * 64 * 2);
     b->act2 = w.take(BT * m.F2 * 64 * 2);
@@ -231,13 +231,13 @@ static int forward(amt_model& m, const float* logmel, int B, int T, float* frame
   // ---- CNN ----
   STAGE("conv1", run_conv1(logmel, F_(m, "conv1.w"), F_(m, "conv1.b"), b.act1, B, c.n_mels, T, s));
   if (large) {
-    STAGE("res1.c1", conv(m, b.act1, 64, nullptr, 0, B, T, m.F1, T_(m, "res1.c1.w"), F_(m, "res1.c1.b"), 64, 3, 3, b.h1, 0, s));
-    STAGE("res1.c2", conv(m, b.h1, 64, b.act1, 64, B, T, m.F1, T_(m, "res1.c2.w"), F_(m, "res1.c2.b"), 64, 3, 3, b.act2, 1, s));
+    STAGE("res1.c1", conv(m, b.act1, 32, nullptr, 0, B, T, m.F1, T_(m, "res1.c1.w"), F_(m, "res1.c1.b"), 64, 3, 3, b.h1, 0, s));
+    STAGE("res1.c2", conv(m, b.h1, 64, b.act1, 32, B, T, m.F1, T_(m, "res1.c2.w"), F_(m, "res1.c2.b"), 64, 3, 3, b.act2, 1, s));
     STAGE("res2.c1", conv(m, b.act2, 64, nullptr, 0, B, T, m.F2, T_(m, "res2.c1.w"), F_(m, "res2.c1.b"), 128, 3, 3, b.h2, 0, s));
     STAGE("res2.c2", conv(m, b.h2, 128, b.act2, 64, B, T, m.F2, T_(m, "res2.c2.w"), F_(m, "res2.c2.b"), 128, 3, 3, b.act3, 0, s));
     STAGE("freq", conv(m, b.act3, 128, nullptr, 0, B, T, m.F2, T_(m, "freq.w"), F_(m, "freq.b"), 256, 7, 3, b.feat, 1, s));
   } else {
-    STAGE("c2", conv(m, b.act1, 64, nullptr, 0, B, T, m.F1, T_(m, "c2.w"), F_(m, "c2.b"), 64, 3, 3, b.feat, 1, s));
+    STAGE("c2", conv(m, b.act1, 32, nullptr, 0, B, T, m.F1, T_(m, "c2.w"), F_(m, "c2.b"), 64, 3, 3, b.feat, 1, s));
   }
 
   // ---- BiLSTM stack (+ the parallel local BiLSTM of the large model on layer 0) ----

@@ -7,66 +7,72 @@ namespace amt {
 // ----------------------------------------------------------------------------
 // conv1: Conv2d(1,32,3x3,pad 1) + BatchNorm(eval, folded) + ReLU + MaxPool(2,1)
 // (reference models/cnn_rnn_model.py:30-33 and :179-182).  K = 9 is not a tensor-core
-// shape: this is a bandwidth-bound stencil.  Reads logmel [B][F][T] f32, writes
-// activations [B][T][F/2][64] bf16 (channels 32..63 are zero padding so that the next
-// layer's K blocks are whole 128-byte swizzle atoms).
+// shape: this is an fp32 stencil whose floor is the 64 B/position bf16 write.  Reads logmel
+// [B][F][T] f32, writes activations [B][T][F/2][32] bf16 (channels-last, 64-byte rows: the next
+// layer's SWIZZLE_64B K block).
+//
+// Thread = (4 output channels, 1 pooled bin), marching along time with a 4x3 register window:
+// per frame 4 shared-memory loads feed 72 FMAs (weights live in registers), and a warp
+// (8 channel groups x 4 bins) stores 256 contiguous bytes.
 // ----------------------------------------------------------------------------
-constexpr int kC1T = 32, kC1F = 16;   // outputs per CTA: 32 frames x 16 pooled bins
+constexpr int kC1T = 64, kC1F = 32;   // outputs per CTA: 64 frames x 32 pooled bins
+constexpr int kC1Rows = 2 * kC1F + 2, kC1Pitch = kC1T + 3;   // 66 input rows, odd pitch (conflict-free)
 
 __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                     int Fin, int T, int Fout) {
-  __shared__ float tile[2 * kC1F + 2][kC1T + 3];     // 34 x 35
-  __shared__ float sw[32 * 9];
-  __shared__ float sb[32];
+  __shared__ float tile[kC1Rows][kC1Pitch];
   const int tid = threadIdx.x;
   const int t0 = blockIdx.x * kC1T, fo0 = blockIdx.y * kC1F, b = blockIdx.z;
-  for (int i = tid; i < 32 * 9; i += 256) sw[i] = w[i];
-  if (tid < 32) sb[tid] = bias[tid];
   const float* xb = x + static_cast<size_t>(b) * Fin * T;
-  for (int i = tid; i < (2 * kC1F + 2) * (kC1T + 2); i += 256) {
+  for (int i = tid; i < kC1Rows * (kC1T + 2); i += 256) {
     const int rr = i / (kC1T + 2), cc = i - rr * (kC1T + 2);
     const int f = 2 * fo0 - 1 + rr, t = t0 - 1 + cc;
     tile[rr][cc] = (f >= 0 && f < Fin && t >= 0 && t < T) ? __ldg(xb + static_cast<size_t>(f) * T + t) : 0.0f;
   }
+  const int lane = tid & 31, warp = tid >> 5;
+  const int cg = lane & 7;                         // channels 4*cg .. 4*cg+3
+  const int fl = warp * 4 + (lane >> 3);           // pooled bin inside the CTA tile
+  float wr[4][9], br[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    br[c] = __ldg(bias + 4 * cg + c);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wr[c][k] = __ldg(w + (4 * cg + c) * 9 + k);   // k = kf*3 + kt
+  }
   __syncthreads();
+  const int fo = fo0 + fl;
+  float win[4][3];                                 // input rows 2*fo-1 .. 2*fo+2, frames t-1 .. t+1
 #pragma unroll
-  for (int rep = 0; rep < 2; ++rep) {
-    const int pos = tid + rep * 256;
-    const int fl = pos & (kC1F - 1), tl = pos >> 4;
-    const int fo = fo0 + fl, t = t0 + tl;
-    float in[4][3];
+  for (int a = 0; a < 4; ++a) {
+    win[a][1] = tile[2 * fl + a][0];
+    win[a][2] = tile[2 * fl + a][1];
+  }
+  __nv_bfloat16* orow = out + ((static_cast<size_t>(b) * T + t0) * Fout + fo) * 32 + 4 * cg;
+  const int tmax = min(kC1T, T - t0);
+  for (int tl = 0; tl < tmax; ++tl) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) in[a][c] = tile[2 * fl + a][tl + c];
-    uint32_t packed[16];
-#pragma unroll
-    for (int c2 = 0; c2 < 16; ++c2) {
-      float r[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int ch = 2 * c2 + u;
-        float a0 = sb[ch], a1 = sb[ch];
-#pragma unroll
-        for (int kf = 0; kf < 3; ++kf)
-#pragma unroll
-          for (int kt = 0; kt < 3; ++kt) {
-            const float wv = sw[ch * 9 + kf * 3 + kt];
-            a0 = fmaf(wv, in[kf][kt], a0);
-            a1 = fmaf(wv, in[kf + 1][kt], a1);
-          }
-        r[u] = fmaxf(fmaxf(a0, a1), 0.0f);
-      }
-      packed[c2] = ptx::pack_bf16(r[0], r[1]);
+    for (int a = 0; a < 4; ++a) {
+      win[a][0] = win[a][1];
+      win[a][1] = win[a][2];
+      win[a][2] = tile[2 * fl + a][tl + 2];
     }
-    if (fo < Fout && t < T) {
-      uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * T + t) * Fout + fo) * 64);
+    float r[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    for (int c = 0; c < 4; ++c) {
+      float a0 = br[c], a1 = br[c];
 #pragma unroll
-      for (int j = 4; j < 8; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+      for (int kf = 0; kf < 3; ++kf)
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          a0 = fmaf(wr[c][kf * 3 + kt], win[kf][kt], a0);
+          a1 = fmaf(wr[c][kf * 3 + kt], win[kf + 1][kt], a1);
+        }
+      r[c] = fmaxf(fmaxf(a0, a1), 0.0f);
     }
+    if (fo < Fout)
+      *reinterpret_cast<uint2*>(orow + static_cast<size_t>(tl) * Fout * 32) =
+          make_uint2(ptx::pack_bf16(r[0], r[1]), ptx::pack_bf16(r[2], r[3]));
   }
 }
 

@@ -7,8 +7,8 @@ Packed names / layouts (all contiguous; "bf16 [N, K]" means K-major rows):
 
   conv1.w  f32 [32, 9]            stem conv, BatchNorm folded, tap = kf*3 + kt
   conv1.b  f32 [32]
-  <conv>.w bf16 [Cout, taps*Cin64 (+Cskip64)]   BN folded; K index = (kf, kt, cin),
-                                  cin zero-padded to a multiple of 64; for residual
+  <conv>.w bf16 [Cout, taps*Cin (+Cskip)]   BN folded; K index = (kf, kt, cin), cin = 32
+                                  (stem output) or a multiple of 64; for residual
                                   blocks the 1x1 skip conv (BN folded) is appended
                                   along K and its bias summed into <conv>.b
   <conv>.b f32 [Cout]
@@ -46,9 +46,10 @@ def _fold_bn(sd, conv: str, bn: str):
 
 
 def _pack_conv_k(w: torch.Tensor) -> torch.Tensor:
-    """[Co, Ci, kf, kt] -> [Co, kf*kt*Ci64] with K index (kf, kt, ci), ci zero-padded to 64."""
+    """[Co, Ci, kf, kt] -> [Co, kf*kt*Cip] with K index (kf, kt, ci); ci is kept when it is 32 (one
+    SWIZZLE_64B block) and zero-padded to a multiple of 64 otherwise."""
     co, ci, kf, kt = w.shape
-    ci64 = (ci + 63) // 64 * 64
+    ci64 = ci if ci == 32 else (ci + 63) // 64 * 64
     out = torch.zeros(co, kf, kt, ci64, dtype=w.dtype, device=w.device)
     out[..., :ci] = w.permute(0, 2, 3, 1)
     return out.reshape(co, kf * kt * ci64)

@@ -51,16 +51,16 @@ def emu_forward(P, x, model_type, n_mels, H, layers, use_attention=True, use_hea
     R = lambda t: _r(t, bf16_acts)
     y = F.conv2d(x, P["conv1.w"].view(32, 1, 3, 3), P["conv1.b"], padding=1).relu()
     y = F.max_pool2d(y, (2, 1)).permute(0, 3, 2, 1)                       # [B,T,F1,32]
-    act1 = R(torch.cat([y, torch.zeros_like(y)], dim=-1))                 # 64 channels, upper half zero
+    act1 = R(y.contiguous())                                              # 32 channels
     if large:
-        h1 = R(emu_conv(act1, P["res1.c1.w"], P["res1.c1.b"], 3, 3, 64))
-        act2 = R(emu_conv(h1, P["res1.c2.w"], P["res1.c2.b"], 3, 3, 64, act1, 64, pool=True))
+        h1 = R(emu_conv(act1, P["res1.c1.w"], P["res1.c1.b"], 3, 3, 32))
+        act2 = R(emu_conv(h1, P["res1.c2.w"], P["res1.c2.b"], 3, 3, 64, act1, 32, pool=True))
         h2 = R(emu_conv(act2, P["res2.c1.w"], P["res2.c1.b"], 3, 3, 64))
         act3 = R(emu_conv(h2, P["res2.c2.w"], P["res2.c2.b"], 3, 3, 128, act2, 64))
         feat = R(emu_conv(act3, P["freq.w"], P["freq.b"], 7, 3, 128, pool=True))
         Hl = H // 2
     else:
-        feat = R(emu_conv(act1, P["c2.w"], P["c2.b"], 3, 3, 64, pool=True))
+        feat = R(emu_conv(act1, P["c2.w"], P["c2.b"], 3, 3, 32, pool=True))
         Hl = 0
     xin = feat.reshape(B, T, -1)
     D = 2 * H + 2 * Hl
