@@ -60,6 +60,9 @@ int ensure_device();                  // AMT_ERR_DEVICE unless cc 10.x
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box,
                      CUtensorMapSwizzle swizzle);
+int encode_tmap_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box,
+                    CUtensorMapSwizzle swizzle);
 
 }  // namespace amt
 

@@ -4,20 +4,6 @@
 
 namespace amt {
 
-struct ConvGemmDesc {
-  const void* X;  int C;            // primary activations [B][T][F][C] bf16
-  const void* X2; int C2;           // optional second source (1x1, centre tap) or nullptr
-  int B, T, F;
-  const void* W;                    // [N][Ktot] bf16, Ktot = kf*kt*C + C2, K index = (tap, channel)
-  const float* bias;                // [N]
-  int N;
-  int kf, kt;
-  void* out; long long ld_out;
-  int relu, pool, out_f32;
-  int boxF, boxT;                   // M tile = boxF x boxT positions (= 128)
-};
-
-int run_conv_gemm(const ConvGemmDesc& d, cudaStream_t stream);
 // halo-tile implicit-GEMM convolution (conv_halo.cu): X [B][T][F][C], optional 1x1 skip source X2 [B][T][F][C2],
 // W [N][kf*kt*C + C2] (K index = (kf, kt, c)), out [B][T][F or F/2][N] bf16
 int run_conv_halo(const void* X, int C, const void* X2, int C2, int B, int T, int F, const void* W, const float* bias,

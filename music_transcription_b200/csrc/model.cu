@@ -201,15 +201,7 @@ static const float* F_(const amt_model& m, const std::string& n) { return static
 
 static int conv(const amt_model&, const void* X, int C, const void* X2, int C2, int B, int T, int F, const void* W,
                 const float* bias, int N, int kf, int kt, void* out, int pool, cudaStream_t s) {
-  static const bool taps = getenv("AMT_CONV_TAPS") != nullptr;     // bring-up switch: tap-by-tap TMA boxes
-  if (!taps) return run_conv_halo(X, C, X2, C2, B, T, F, W, bias, N, kf, kt, out, 1, pool, s);
-  ConvGemmDesc d{};
-  d.X = X; d.C = C; d.X2 = X2; d.C2 = C2;
-  d.B = B; d.T = T; d.F = F;
-  d.W = W; d.bias = bias; d.N = N; d.kf = kf; d.kt = kt;
-  d.out = out; d.ld_out = N; d.relu = 1; d.pool = pool; d.out_f32 = 0;
-  d.boxF = 16; d.boxT = 8;
-  return run_conv_gemm(d, s);
+  return run_conv_halo(X, C, X2, C2, B, T, F, W, bias, N, kf, kt, out, 1, pool, s);
 }
 
 static int forward(amt_model& m, const float* logmel, int B, int T, float* frame, float* onset, float* offset,

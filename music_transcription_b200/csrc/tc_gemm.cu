@@ -1,36 +1,26 @@
-// tcgen05 / TMA / TMEM persistent implicit-GEMM for sm_100a.
+// tcgen05 / TMA / TMEM persistent GEMM for sm_100a:  C[M][N] = A[M][K] * W[N][K]^T + bias  (bf16 in,
+// fp32 accumulate, bf16 or f32 out, optional ReLU).
 //
-// One kernel serves every dense contraction on the path:
-//   * the 3x3 / 7x3 convolutions of the CNN (reference models/cnn_rnn_model.py:35-38,
-//     :83-99, :196-201) as implicit GEMM over NHWC-like activations [B][T][F][C]:
-//     for every filter tap the A tile is ONE shifted 4-D TMA box (zero fill outside
-//     the tensor = the conv's zero padding), so no im2col buffer ever exists;
-//   * the residual 1x1 skip conv (:88-92) as extra K blocks from a second tensor map,
-//     accumulated into the same TMEM tile (BatchNorm is folded into the weights);
-//   * all nn.Linear / LSTM input projections (:45-55, :212-260) as the 1-tap case.
+// Serves every nn.Linear of the path and the LSTM input projections (reference
+// models/cnn_rnn_model.py:45-55, :212-260): x_t W_ih^T for all t at once, qkv / proj of the
+// attention block, shared_fc and the stacked frame|onset|offset heads.  (The convolutions have their
+// own halo-tile kernel, conv_halo.cu.)
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
-// warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU/freq-max-pool -> global).  The
-// accumulator is double buffered in TMEM so the epilogue of tile i overlaps the
-// MMAs of tile i+1.  Tile = 128 (M) x BN (N), BLOCK_K = 64 bf16 = one 128-B swizzle atom.
-#include <cstdlib>
-
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 =
+// epilogue.  Tile = 128 (M) x BN (N), BLOCK_K = 64 bf16 = one 128-B swizzle atom, 4-6 smem stages,
+// double-buffered TMEM accumulator (the epilogue of tile i overlaps the MMAs of tile i+1).
+// Epilogue: two warps per TMEM lane quarter; each 128-byte-wide column chunk of the tile is staged in
+// a swizzled shared-memory buffer (double buffered) and written by ONE TMA tensor store, which also
+// clips the rows beyond M -- the warps never issue global stores themselves.
 #include "kernels.cuh"
 
 namespace amt {
 
 struct GemmParams {
-  int kblocks0, cblk0, ntapT, padF, padT;
-  int kblocks1;
-  int boxF_log2, boxT;
-  int F, T, Bn;
-  int tilesF, tilesT, n_tiles, num_tiles;
-  int m_tiles, group_n;   // rasterisation: n-tiles are swept in groups of group_n (weight slab stays in L2)
+  int kblocks;
+  int n_tiles, m_tiles, num_tiles, group_n;   // rasterisation: n-tiles are swept in groups of group_n
   const float* bias;
-  void* out;
-  long long ld_out;
-  int Fout;
-  int pool, relu;
+  int relu;
 };
 
 // tile id -> (m tile, n tile).  n-tiles are visited in groups of group_n: inside a group the order is
@@ -48,6 +38,10 @@ __device__ __forceinline__ int decode_tile(const GemmParams& p, int tile, int& m
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kGemmThreads = 320;
+constexpr int kGemmEpiWarp0 = 2;
+constexpr int kGemmEpiThreads = 256;
+constexpr int kOutChunkBytes = 128 * 128;        // one staged chunk: 128 rows x 128 bytes
 
 template <int BN>
 struct GemmCfg {
@@ -55,17 +49,20 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kOutChunkBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, bool OUT_F32>
-__global__ void __launch_bounds__(192, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+__global__ void __launch_bounds__(kGemmThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
+  constexpr int kChunkCols = OUT_F32 ? 32 : 64;          // output columns per 128-byte staged row
+  constexpr int kWarpCols = kChunkCols / 2;              // columns per epilogue warp and chunk
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* o_smem = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(o_smem + 2 * kOutChunkBytes);
   uint64_t* empty = full + Cfg::kStages;
   uint64_t* tfull = empty + Cfg::kStages;
   uint64_t* tempty = tfull + 2;
@@ -75,9 +72,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmA0);
-    ptx::prefetch_tmap(&tmA1);
+    ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmC);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -87,7 +84,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&tfull[i], 1);
-        ptx::mbar_init(&tempty[i], 4);
+        ptx::mbar_init(&tempty[i], 8);
       }
       ptx::mbar_fence_init();
     }
@@ -100,47 +97,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int kblocks = p.kblocks0 + p.kblocks1;
-  const int boxF = 1 << p.boxF_log2;
-
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     // The whole warp runs the (warp-uniform) loop; only the issuing instructions are predicated on
     // one elected lane, so coordinates / addresses stay in uniform registers.
     const bool leader = ptx::elect_one_sync();
-    // all per-k-block state is carried incrementally (no div/mod in the loop: the producer must stay
-    // well under the 128-cycle MMA time of a BN=64 k-block)
     uint32_t s = 0, ph = 0;
     uint8_t* a_dst = smem;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int m;
       const int n0 = decode_tile(p, tile, m) * BN;
-      const int f0 = (m % p.tilesF) * boxF;
-      m /= p.tilesF;
-      const int t0 = (m % p.tilesT) * p.boxT;
-      const int b = m / p.tilesT;
-      int cb = 0, kt = 0;
-      int c1 = f0 - p.padF;                   // f coordinate of the current tap row
-      for (int kb = 0; kb < kblocks; ++kb) {
+      const int m0 = m * kBlockM;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
         ptx::mbar_wait(&empty[s], ph ^ 1);
-        const bool first = kb < p.kblocks0;
-        const CUtensorMap* am = first ? &tmA0 : &tmA1;
-        const int c0 = first ? cb * kBlockK : (kb - p.kblocks0) * kBlockK;
-        const int cf = first ? c1 : f0;
-        const int ct = first ? t0 + kt - p.padT : t0;
         if (leader) {
           ptx::mbar_expect_tx(&full[s], Cfg::kStageBytes);
-          ptx::tma_load_4d(a_dst, am, &full[s], c0, cf, ct, b);
+          ptx::tma_load_2d(a_dst, &tmA, &full[s], kb * kBlockK, m0);
           ptx::tma_load_2d(a_dst + kABytes, &tmB, &full[s], kb * kBlockK, n0);
         }
         __syncwarp();
-        if (++cb == p.cblk0) {                // next tap: (kf, kt) row-major
-          cb = 0;
-          if (++kt == p.ntapT) {
-            kt = 0;
-            ++c1;
-          }
-        }
         a_dst += Cfg::kStageBytes;
         if (++s == Cfg::kStages) {
           s = 0;
@@ -162,7 +137,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::mbar_wait(&tempty[acc], aph ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = 0; kb < p.kblocks; ++kb) {
         ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
         // descriptors differ only in the 14-bit start-address field (units of 16 bytes)
@@ -186,68 +161,75 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
-    const int q = warp & 3;              // TMEM lane quarter this warp may read
-    uint32_t tl = 0;
+    const int q = warp & 3;                          // TMEM lane quarter this warp may read
+    const int half = (warp - kGemmEpiWarp0) >> 2;    // which half of every 128-byte column chunk
+    const bool issuer = threadIdx.x == kGemmEpiWarp0 * 32;
+    const int r = q * 32 + lane;                     // tile row
+    const uint32_t o_row = static_cast<uint32_t>(r) * 128u;
+    uint32_t tl = 0, chunk_no = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
       int m;
       const int n0 = decode_tile(p, tile, m) * BN;
-      const int f0 = (m % p.tilesF) * boxF;
-      m /= p.tilesF;
-      const int t0 = (m % p.tilesT) * p.boxT;
-      const int b = m / p.tilesT;
+      const int m0 = m * kBlockM;
       const uint32_t acc = tl & 1;
-      const uint32_t aph = (tl >> 1) & 1;
-
-      const int r = q * 32 + lane;
-      const int fl = r & (boxF - 1);
-      const int f = f0 + fl;
-      const int t = t0 + (r >> p.boxF_log2);
-      bool ok = (f < p.F) && (t < p.T);
-      long long orow;
-      if (p.pool) {
-        ok = ok && ((fl & 1) == 0) && (f + 1 < p.F);
-        orow = (static_cast<long long>(b) * p.T + t) * p.Fout + (f >> 1);
-      } else {
-        orow = (static_cast<long long>(b) * p.T + t) * p.Fout + f;
-      }
-
-      ptx::mbar_wait(&tfull[acc], aph);
+      ptx::mbar_wait(&tfull[acc], (tl >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * kWarpCols;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+      for (int c = 0; c < BN / kChunkCols; ++c, ++chunk_no) {
+        uint32_t v[kWarpCols];
+        ptx::tmem_ld_cols<kWarpCols>(taddr + c * kChunkCols, v);
         ptx::tmem_ld_wait();
-        float x[32];
-        const float* bias = p.bias + n0 + c * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          x[j] = __uint_as_float(v[j]) + __ldg(bias + j);
-          if (p.relu) x[j] = fmaxf(x[j], 0.0f);
+        if (c == BN / kChunkCols - 1) {              // accumulator fully read: hand it back to the MMA warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
         }
-        if (p.pool) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c * kChunkCols + half * kWarpCols);
+        uint8_t* obuf = o_smem + (chunk_no & 1) * kOutChunkBytes;
+        uint4 pk[4];
+        if constexpr (OUT_F32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], __shfl_xor_sync(0xffffffffu, x[j], 1));
-        }
-        if (ok) {
-          if (OUT_F32) {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ld_out + n0 + c * 32);
+          for (int j = 0; j < 4; ++j) {
+            const float4 bb = __ldg(b4 + j);
+            float x0 = __uint_as_float(v[4 * j]) + bb.x, x1 = __uint_as_float(v[4 * j + 1]) + bb.y;
+            float x2 = __uint_as_float(v[4 * j + 2]) + bb.z, x3 = __uint_as_float(v[4 * j + 3]) + bb.w;
+            if (p.relu) {
+              x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); x2 = fmaxf(x2, 0.0f); x3 = fmaxf(x3, 0.0f);
+            }
+            pk[j] = make_uint4(__float_as_uint(x0), __float_as_uint(x1), __float_as_uint(x2), __float_as_uint(x3));
+          }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.ld_out + n0 + c * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(ptx::pack_bf16(x[8 * j], x[8 * j + 1]), ptx::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                                  ptx::pack_bf16(x[8 * j + 4], x[8 * j + 5]), ptx::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+          for (int j = 0; j < 4; ++j) {
+            const float4 ba = __ldg(b4 + 2 * j), bb = __ldg(b4 + 2 * j + 1);
+            float x0 = __uint_as_float(v[8 * j]) + ba.x, x1 = __uint_as_float(v[8 * j + 1]) + ba.y;
+            float x2 = __uint_as_float(v[8 * j + 2]) + ba.z, x3 = __uint_as_float(v[8 * j + 3]) + ba.w;
+            float x4 = __uint_as_float(v[8 * j + 4]) + bb.x, x5 = __uint_as_float(v[8 * j + 5]) + bb.y;
+            float x6 = __uint_as_float(v[8 * j + 6]) + bb.z, x7 = __uint_as_float(v[8 * j + 7]) + bb.w;
+            if (p.relu) {
+              x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); x2 = fmaxf(x2, 0.0f); x3 = fmaxf(x3, 0.0f);
+              x4 = fmaxf(x4, 0.0f); x5 = fmaxf(x5, 0.0f); x6 = fmaxf(x6, 0.0f); x7 = fmaxf(x7, 0.0f);
+            }
+            pk[j] = make_uint4(ptx::pack_bf16(x0, x1), ptx::pack_bf16(x2, x3), ptx::pack_bf16(x4, x5), ptx::pack_bf16(x6, x7));
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t c16 = static_cast<uint32_t>(half * 4 + j);
+          *reinterpret_cast<uint4*>(obuf + o_row + ((c16 ^ (r & 7)) << 4)) = pk[j];
+        }
+        ptx::fence_proxy_async_smem();
+        // the buffer written NEXT (other parity) was last read by the store issued one chunk ago
+        if (issuer) ptx::bulk_wait_group_read0();
+        ptx::named_bar_sync(1, kGemmEpiThreads);
+        if (issuer) {
+          ptx::tma_store_2d(&tmC, obuf, n0 + c * kChunkCols, m0);
+          ptx::bulk_commit_group();
+        }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
     }
+    if (issuer) ptx::bulk_wait_group0();             // all output stores complete before the CTA exits
   }
 
   ptx::tc_fence_before();
@@ -262,7 +244,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // host side
 // ----------------------------------------------------------------------------
 template <int BN, bool OUT_F32>
-static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmParams& p,
                   cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
@@ -272,93 +254,63 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     attr_set = true;
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  tc_gemm_kernel<BN, OUT_F32><<<grid, 192, Cfg::kSmemBytes, stream>>>(a0, a1, b, p);
+  tc_gemm_kernel<BN, OUT_F32><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, c, p);
   AMT_CHECK_LAUNCH();
   return 0;
 }
 
-int run_conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
+int run_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, long long ldc, int relu,
+             int out_f32, cudaStream_t stream) {
   AMT_TRY(ensure_device());
-  AMT_REQUIRE(d.C % 64 == 0 && (d.X2 == nullptr || d.C2 % 64 == 0), "conv/gemm: channel counts must be multiples of 64");
-  AMT_REQUIRE(d.N % 64 == 0, "conv/gemm: N (%d) must be a multiple of 64", d.N);
-  AMT_REQUIRE(d.boxF * d.boxT == kBlockM && (d.boxF & (d.boxF - 1)) == 0, "conv/gemm: bad M-tile box");
-  AMT_REQUIRE(d.B > 0 && d.T > 0 && d.F > 0, "conv/gemm: empty problem");
-  const int BN = d.N % 256 == 0 ? 256 : (d.N % 128 == 0 ? 128 : 64);
-  const int c2 = d.X2 ? d.C2 : 0;
-  const long long Ktot = static_cast<long long>(d.kf) * d.kt * d.C + c2;
+  AMT_REQUIRE(M > 0, "gemm: empty problem");
+  AMT_REQUIRE(K % 64 == 0 && K > 0, "gemm: K (%d) must be a positive multiple of 64", K);
+  AMT_REQUIRE(N % 64 == 0 && N > 0, "gemm: N (%d) must be a positive multiple of 64", N);
+  const int esize = out_f32 ? 4 : 2;
+  AMT_REQUIRE(ldc >= N && (ldc * esize) % 16 == 0, "gemm: ldc (%lld) must be >= N with 16-byte aligned rows", ldc);
+  AMT_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+              "gemm: C and bias must be 16-byte aligned");
+  const int BN = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
 
-  CUtensorMap a0, a1, bm;
+  CUtensorMap am, bm, cm;
   {
-    uint64_t dims[4] = {(uint64_t)d.C, (uint64_t)d.F, (uint64_t)d.T, (uint64_t)d.B};
-    uint64_t str[3] = {(uint64_t)d.C * 2, (uint64_t)d.F * d.C * 2, (uint64_t)d.T * d.F * d.C * 2};
-    uint32_t box[4] = {64, (uint32_t)d.boxF, (uint32_t)d.boxT, 1};
-    AMT_TRY(encode_tmap_bf16(&a0, d.X, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
-  }
-  if (d.X2) {
-    uint64_t dims[4] = {(uint64_t)d.C2, (uint64_t)d.F, (uint64_t)d.T, (uint64_t)d.B};
-    uint64_t str[3] = {(uint64_t)d.C2 * 2, (uint64_t)d.F * d.C2 * 2, (uint64_t)d.T * d.F * d.C2 * 2};
-    uint32_t box[4] = {64, (uint32_t)d.boxF, (uint32_t)d.boxT, 1};
-    AMT_TRY(encode_tmap_bf16(&a1, d.X2, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
-  } else {
-    a1 = a0;
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {64, 128};
+    AMT_TRY(encode_tmap_bf16(&am, A, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   {
-    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)d.N};
-    uint64_t str[1] = {(uint64_t)Ktot * 2};
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)K * 2};
     uint32_t box[2] = {64, (uint32_t)BN};
-    AMT_TRY(encode_tmap_bf16(&bm, d.W, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    AMT_TRY(encode_tmap_bf16(&bm, W, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)ldc * esize};
+    uint32_t box[2] = {(uint32_t)(out_f32 ? 32 : 64), 128};
+    if (out_f32) AMT_TRY(encode_tmap_f32(&cm, C, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    else AMT_TRY(encode_tmap_bf16(&cm, C, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
 
   GemmParams p;
-  p.cblk0 = d.C / 64;
-  p.kblocks0 = d.kf * d.kt * p.cblk0;
-  p.ntapT = d.kt;
-  p.padF = d.kf / 2;
-  p.padT = d.kt / 2;
-  p.kblocks1 = c2 / 64;
-  p.boxF_log2 = 0;
-  while ((1 << p.boxF_log2) < d.boxF) ++p.boxF_log2;
-  p.boxT = d.boxT;
-  p.F = d.F;
-  p.T = d.T;
-  p.Bn = d.B;
-  p.tilesF = ceil_div(d.F, d.boxF);
-  p.tilesT = ceil_div(d.T, d.boxT);
-  p.n_tiles = d.N / BN;
-  p.m_tiles = d.B * p.tilesF * p.tilesT;
+  p.kblocks = K / 64;
+  p.n_tiles = N / BN;
+  p.m_tiles = ceil_div(M, kBlockM);
   p.group_n = p.n_tiles > 8 ? 8 : p.n_tiles;
-  const long long nt = static_cast<long long>(d.B) * p.tilesF * p.tilesT * p.n_tiles;
-  AMT_REQUIRE(nt < (1ll << 31), "conv/gemm: too many tiles");
+  const long long nt = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  AMT_REQUIRE(nt < (1ll << 31), "gemm: too many tiles");
   p.num_tiles = static_cast<int>(nt);
-  p.bias = d.bias;
-  p.out = d.out;
-  p.ld_out = d.ld_out;
-  p.pool = d.pool;
-  p.relu = d.relu;
-  p.Fout = d.pool ? d.F / 2 : d.F;
+  p.bias = bias;
+  p.relu = relu;
 
-  if (d.out_f32) {
-    if (BN == 256) return launch<256, true>(a0, a1, bm, p, stream);
-    if (BN == 128) return launch<128, true>(a0, a1, bm, p, stream);
-    return launch<64, true>(a0, a1, bm, p, stream);
+  if (out_f32) {
+    if (BN == 256) return launch<256, true>(am, bm, cm, p, stream);
+    if (BN == 128) return launch<128, true>(am, bm, cm, p, stream);
+    return launch<64, true>(am, bm, cm, p, stream);
   }
-  if (BN == 256) return launch<256, false>(a0, a1, bm, p, stream);
-  if (BN == 128) return launch<128, false>(a0, a1, bm, p, stream);
-  return launch<64, false>(a0, a1, bm, p, stream);
-}
-
-int run_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, long long ldc, int relu,
-             int out_f32, cudaStream_t stream) {
-  AMT_REQUIRE(K % 64 == 0, "gemm: K (%d) must be a multiple of 64", K);
-  ConvGemmDesc d{};
-  d.X = A; d.C = K; d.X2 = nullptr; d.C2 = 0;
-  d.B = 1; d.T = 1; d.F = M;
-  d.W = W; d.bias = bias; d.N = N;
-  d.kf = 1; d.kt = 1;
-  d.out = C; d.ld_out = ldc;
-  d.relu = relu; d.pool = 0; d.out_f32 = out_f32;
-  d.boxF = 128; d.boxT = 1;
-  return run_conv_gemm(d, stream);
+  if (BN == 256) return launch<256, false>(am, bm, cm, p, stream);
+  if (BN == 128) return launch<128, false>(am, bm, cm, p, stream);
+  return launch<64, false>(am, bm, cm, p, stream);
 }
 
 }  // namespace amt
@@ -372,19 +324,8 @@ int amt_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int 
 
 int amt_conv_bf16(const void* X, const void* X2, const void* W, const float* bias, void* Y, int B, int T, int F,
                   int Cin, int Cin2, int Cout, int kf, int kt, int relu, int pool, amt_stream_t stream) {
-  static const bool taps = getenv("AMT_CONV_TAPS") != nullptr;     // bring-up switch: tap-by-tap TMA boxes
-  if (!taps)
-    return amt::run_conv_halo(X, Cin, X2, Cin2, B, T, F, W, bias, Cout, kf, kt, Y, relu, pool,
-                              static_cast<cudaStream_t>(stream));
-  amt::ConvGemmDesc d{};
-  d.X = X; d.C = Cin; d.X2 = X2; d.C2 = Cin2;
-  d.B = B; d.T = T; d.F = F;
-  d.W = W; d.bias = bias; d.N = Cout;
-  d.kf = kf; d.kt = kt;
-  d.out = Y; d.ld_out = Cout;
-  d.relu = relu; d.pool = pool; d.out_f32 = 0;
-  d.boxF = 16; d.boxT = 8;
-  return amt::run_conv_gemm(d, static_cast<cudaStream_t>(stream));
+  return amt::run_conv_halo(X, Cin, X2, Cin2, B, T, F, W, bias, Cout, kf, kt, Y, relu, pool,
+                            static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
