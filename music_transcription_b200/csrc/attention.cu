@@ -6,8 +6,12 @@
 // plain running sum (no running-max rescaling) is exact in fp32; keys beyond T are
 // masked explicitly (a padded zero logit would contribute e^0, not 0).
 //
-// v1 uses warp-level mma.sync (m16n8k16 bf16, fp32 accumulate): 64 queries per CTA
-// (4 warps x 16 rows), key/value blocks of 64 staged in shared memory with cp.async.
+// This file is the generic fallback for head dims that are not a multiple of 64 (hidden sizes other
+// than 512): warp-level mma.sync (m16n8k16 bf16, fp32 accumulate), 64 queries per CTA (4 warps x 16
+// rows), key/value blocks of 64 staged in shared memory with cp.async.  Head dims 64/128/192 (the
+// canonical model: 8 x 192) run the tcgen05 kernel in attention_tc.cu.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace amt {
@@ -185,6 +189,9 @@ static int launch_attention(const void* qkv, void* out, int B, int T, int heads,
 int run_attention(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip, cudaStream_t stream) {
   AMT_TRY(ensure_device());
   AMT_REQUIRE(B > 0 && T > 0 && heads > 0, "attention: empty problem");
+  static const bool force_sync = getenv("AMT_ATT_MMA_SYNC") != nullptr;    // bring-up switch
+  if (!force_sync && (head_dim == 64 || head_dim == 128 || head_dim == 192))
+    return run_attention_tc(qkv, out, B, T, heads, head_dim, clip, stream);
   switch (head_dim) {
     case 48: return launch_attention<48>(qkv, out, B, T, heads, clip, stream);
     case 96: return launch_attention<96>(qkv, out, B, T, heads, clip, stream);

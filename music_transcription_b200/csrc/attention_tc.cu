@@ -1,0 +1,363 @@
+// tcgen05 / TMA / TMEM fused clamped-softmax attention for sm_100a (head_dim a multiple of 64; the
+// canonical model has 8 heads x 192).  Reference models/cnn_rnn_model.py:118-139, the part between the
+// qkv and proj Linear layers:
+//     S = clamp(Q K^T * hd^-0.5, -clip, +clip);  P = softmax(S);  O = P V
+//
+// Because the logits are clamped to +-clip (= 10) BEFORE the softmax, exp() is bounded by e^+-10 and a
+// plain running sum is exact in fp32: no running maximum, so the un-normalised O accumulates in tensor
+// memory over all key blocks without ever being rescaled, and the T x T scores never leave the SM.
+//
+// One tile = 128 queries of one (chunk, head); keys/values stream in blocks of 64.
+//   warp 0   TMA loader: Q once per tile, K and V blocks through two 2-deep rings
+//   warp 1   MMA issuer:  S_j = Q K_j^T        (M 128, N 64,  K = hd)   -> TMEM S[j&1]
+//                         O  += P_j V_j        (M 128, N hd,  K = 64)   -> TMEM O
+//            V is consumed as it lies in memory ([key][hd], hd contiguous) as an MN-major B operand,
+//            so no transposed copy of V exists; S_{j+1} is issued before O += P_j V_j so the tensor
+//            pipe works while the softmax warps turn S_j into P_j.
+//   warps 3-10  softmax: tcgen05.ld S (two warps per TMEM lane quarter, 32 keys each), scale, clamp,
+//            exp, mask keys >= T, row sums in fp32, P as bf16 into a swizzled smem A-operand tile;
+//            at the end of the tile O / rowsum -> bf16 -> smem -> TMA store (rows >= T clipped).
+// Persistent over (chunk, head, query tile); every ring is indexed by a global key-block counter.
+#include "kernels.cuh"
+
+namespace amt {
+
+constexpr int kAttQ = 128;          // queries per tile
+constexpr int kAttK = 64;           // keys per block
+constexpr int kAttThreads = 352;
+constexpr int kAttSoftWarp0 = 3;
+constexpr int kAttSoftThreads = 256;
+
+struct AttParams {
+  int T, heads, B, q_tiles, num_tiles, nb;     // nb = key blocks per tile
+  int D;                                       // heads * hd
+  float scale, clip;
+};
+
+template <int HD>
+struct AttCfg {
+  static constexpr int kNB = HD / 64;                       // 64-wide head-dim blocks
+  static constexpr int kQBytes = kNB * kAttQ * 128;         // Q tile
+  static constexpr int kKVBytes = kNB * kAttK * 128;        // one K (or V) block
+  static constexpr int kPBytes = kAttQ * 128;               // one P block (128 q x 64 keys)
+  static constexpr int kSmemBytes = kQBytes + 4 * kKVBytes + 2 * kPBytes + 2 * kAttQ * 4 + 1024 + 256;
+  static constexpr int kColO = 128;                         // TMEM: S0 [0,64), S1 [64,128), O [128, 128+HD)
+  static constexpr int kTmemCols = 512;
+};
+
+// kind::f16 instruction descriptor with an MN-major B operand (bit 16)
+__host__ __device__ constexpr uint32_t att_idesc_b_mn(int M, int N) { return ptx::umma_idesc_bf16(M, N) | (1u << 16); }
+
+// MN-major, 128-byte-swizzled operand: 64-element MN atoms `lbo` bytes apart, 8-row K groups 1024 B apart
+__device__ __forceinline__ uint64_t att_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kAttThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const __grid_constant__ CUtensorMap tmO, const AttParams p) {
+  using Cfg = AttCfg<HD>;
+  constexpr int NB = Cfg::kNB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* k_smem = q_smem + Cfg::kQBytes;                  // 2 stages
+  uint8_t* v_smem = k_smem + 2 * Cfg::kKVBytes;             // 2 stages
+  uint8_t* p_smem = v_smem + 2 * Cfg::kKVBytes;             // 2 buffers (also the output staging)
+  float* lsum_x = reinterpret_cast<float*>(p_smem + 2 * Cfg::kPBytes);   // [2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lsum_x + 2 * kAttQ);
+  uint64_t* q_full = bars;          // [1]
+  uint64_t* q_empty = bars + 1;     // [1]
+  uint64_t* k_full = bars + 2;      // [2]
+  uint64_t* k_empty = bars + 4;
+  uint64_t* v_full = bars + 6;
+  uint64_t* v_empty = bars + 8;
+  uint64_t* s_full = bars + 10;
+  uint64_t* s_empty = bars + 12;
+  uint64_t* p_full = bars + 14;
+  uint64_t* p_empty = bars + 16;
+  uint64_t* o_full = bars + 18;     // [1]
+  uint64_t* o_empty = bars + 19;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmKV);
+    ptx::prefetch_tmap(&tmO);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      ptx::mbar_init(q_full, 1);
+      ptx::mbar_init(q_empty, 1);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&k_full[i], 1);
+        ptx::mbar_init(&k_empty[i], 1);
+        ptx::mbar_init(&v_full[i], 1);
+        ptx::mbar_init(&v_empty[i], 1);
+        ptx::mbar_init(&s_full[i], 1);
+        ptx::mbar_init(&s_empty[i], 8);
+        ptx::mbar_init(&p_full[i], 8);
+        ptx::mbar_init(&p_empty[i], 1);
+      }
+      ptx::mbar_init(o_full, 1);
+      ptx::mbar_init(o_empty, 8);
+      ptx::mbar_fence_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA loader ------------------------------
+    const bool leader = ptx::elect_one_sync();
+    uint32_t g = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      int m = tile;
+      const int t0 = (m % p.q_tiles) * kAttQ;
+      m /= p.q_tiles;
+      const int head = m % p.heads;
+      const int b = m / p.heads;
+      ptx::mbar_wait(q_empty, (tl & 1) ^ 1);
+      if (leader) {
+        ptx::mbar_expect_tx(q_full, Cfg::kQBytes);
+        for (int i = 0; i < NB; ++i) ptx::tma_load_3d(q_smem + i * (kAttQ * 128), &tmQ, q_full, head * HD + i * 64, t0, b);
+      }
+      __syncwarp();
+      for (int j = 0; j < p.nb; ++j, ++g) {
+        const uint32_t s = g & 1, ph = (g >> 1) & 1;
+        ptx::mbar_wait(&k_empty[s], ph ^ 1);
+        if (leader) {
+          ptx::mbar_expect_tx(&k_full[s], Cfg::kKVBytes);
+          for (int i = 0; i < NB; ++i)
+            ptx::tma_load_3d(k_smem + s * Cfg::kKVBytes + i * (kAttK * 128), &tmKV, &k_full[s], p.D + head * HD + i * 64,
+                             j * kAttK, b);
+        }
+        __syncwarp();
+        ptx::mbar_wait(&v_empty[s], ph ^ 1);
+        if (leader) {
+          ptx::mbar_expect_tx(&v_full[s], Cfg::kKVBytes);
+          for (int i = 0; i < NB; ++i)
+            ptx::tma_load_3d(v_smem + s * Cfg::kKVBytes + i * (kAttK * 128), &tmKV, &v_full[s],
+                             2 * p.D + head * HD + i * 64, j * kAttK, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    const bool leader = ptx::elect_one_sync();
+    constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(kAttQ, kAttK);
+    constexpr uint32_t idesc_o = att_idesc_b_mn(kAttQ, HD);
+    const uint64_t q_desc = ptx::umma_desc_sw128(ptx::smem_u32(q_smem));
+    const uint64_t k_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(k_smem));
+    const uint64_t p_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(p_smem));
+    const uint64_t v_desc0 = att_desc_mn(ptx::smem_u32(v_smem), kAttK * 128);
+    const uint32_t o_tmem = tmem_base + Cfg::kColO;
+    uint32_t g = 0, tl = 0;
+    // O += P_g V_g for global block gp
+    auto issue_pv = [&](uint32_t gp, bool first_of_tile) {
+      const uint32_t s = gp & 1, ph = (gp >> 1) & 1;
+      ptx::mbar_wait(&p_full[s], ph);
+      ptx::mbar_wait(&v_full[s], ph);
+      if (first_of_tile) ptx::mbar_wait(o_empty, (tl & 1) ^ 1);    // previous tile's O has been read out
+      ptx::tc_fence_after();
+      if (leader) {
+        const uint64_t pd = p_desc0 + static_cast<uint64_t>((s * Cfg::kPBytes) >> 4);
+        const uint64_t vd = v_desc0 + static_cast<uint64_t>((s * Cfg::kKVBytes) >> 4);
+#pragma unroll
+        for (int k = 0; k < kAttK / 16; ++k)       // 16 keys per MMA: 32 B along a P row, 2 KB down the V block
+          ptx::umma_bf16_ss(o_tmem, pd + 2 * k, vd + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o,
+                            (first_of_tile && k == 0) ? 0u : 1u);
+        ptx::umma_commit(&p_empty[s]);
+        ptx::umma_commit(&v_empty[s]);
+      }
+      __syncwarp();
+    };
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      ptx::mbar_wait(q_full, tl & 1);
+      for (int j = 0; j < p.nb; ++j, ++g) {
+        const uint32_t s = g & 1, ph = (g >> 1) & 1;
+        ptx::mbar_wait(&k_full[s], ph);
+        ptx::mbar_wait(&s_empty[s], ph ^ 1);
+        ptx::tc_fence_after();
+        if (leader) {
+          const uint64_t kd = k_desc0 + static_cast<uint64_t>((s * Cfg::kKVBytes) >> 4);
+#pragma unroll
+          for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16_ss(tmem_base + s * kAttK, q_desc + static_cast<uint64_t>(i * ((kAttQ * 128) >> 4) + 2 * k),
+                                kd + static_cast<uint64_t>(i * ((kAttK * 128) >> 4) + 2 * k), idesc_s, (i | k) != 0 ? 1u : 0u);
+          ptx::umma_commit(&k_empty[s]);
+          ptx::umma_commit(&s_full[s]);
+          if (j == p.nb - 1) ptx::umma_commit(q_empty);
+        }
+        __syncwarp();
+        if (j > 0) issue_pv(g - 1, j == 1);
+      }
+      issue_pv(g - 1, p.nb == 1);
+      if (leader) ptx::umma_commit(o_full);
+      __syncwarp();
+    }
+  } else if (warp >= kAttSoftWarp0) {
+    // ------------------------------ softmax + output ------------------------------
+    const int q = warp & 3;                        // TMEM lane quarter
+    const int half = (warp - kAttSoftWarp0) >> 2;  // keys (and output columns) [32*half, 32*half+32) of each 64
+    const bool issuer = threadIdx.x == kAttSoftWarp0 * 32;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f, cl2 = p.clip * 1.4426950408889634f;   // work in log2 units
+    uint32_t g = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      int m = tile;
+      const int t0 = (m % p.q_tiles) * kAttQ;
+      m /= p.q_tiles;
+      const int head = m % p.heads;
+      const int b = m / p.heads;
+      float lsum = 0.0f;
+      for (int j = 0; j < p.nb; ++j, ++g) {
+        const uint32_t s = g & 1, ph = (g >> 1) & 1;
+        ptx::mbar_wait(&s_full[s], ph);
+        ptx::tc_fence_after();
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + s * kAttK + half * 32, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&s_empty[s]);
+        const int key0 = j * kAttK + half * 32;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x0 = fminf(fmaxf(__uint_as_float(v[2 * i]) * sl2, -cl2), cl2);
+          const float x1 = fminf(fmaxf(__uint_as_float(v[2 * i + 1]) * sl2, -cl2), cl2);
+          const float p0 = key0 + 2 * i < p.T ? ptx::ex2_approx(x0) : 0.0f;
+          const float p1 = key0 + 2 * i + 1 < p.T ? ptx::ex2_approx(x1) : 0.0f;
+          lsum += p0 + p1;
+          pk[i] = ptx::pack_bf16(p0, p1);
+        }
+        ptx::mbar_wait(&p_empty[s], ph ^ 1);       // O += P_{g-2} V_{g-2} has consumed this buffer
+        uint8_t* pbuf = p_smem + s * Cfg::kPBytes;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(pbuf + ptx::sw128_offset(row, half * 4 + c)) =
+              make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[s]);
+      }
+      // ---- tile epilogue: O / rowsum -> bf16 -> smem -> TMA store ----
+      lsum_x[half * kAttQ + row] = lsum;
+      ptx::mbar_wait(o_full, tl & 1);              // every MMA of the tile retired: P buffers are free too
+      ptx::tc_fence_after();
+      ptx::named_bar_sync(1, kAttSoftThreads);
+      const float inv = 1.0f / (lsum_x[row] + lsum_x[kAttQ + row]);
+#pragma unroll 1
+      for (int cc = 0; cc < NB; ++cc) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + Cfg::kColO + cc * 64 + half * 32, v);
+        ptx::tmem_ld_wait();
+        if (cc == NB - 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(o_empty);
+        }
+        uint8_t* obuf = p_smem + (cc & 1) * Cfg::kPBytes;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 val = make_uint4(
+              ptx::pack_bf16(__uint_as_float(v[8 * c]) * inv, __uint_as_float(v[8 * c + 1]) * inv),
+              ptx::pack_bf16(__uint_as_float(v[8 * c + 2]) * inv, __uint_as_float(v[8 * c + 3]) * inv),
+              ptx::pack_bf16(__uint_as_float(v[8 * c + 4]) * inv, __uint_as_float(v[8 * c + 5]) * inv),
+              ptx::pack_bf16(__uint_as_float(v[8 * c + 6]) * inv, __uint_as_float(v[8 * c + 7]) * inv));
+          *reinterpret_cast<uint4*>(obuf + ptx::sw128_offset(row, half * 4 + c)) = val;
+        }
+        ptx::fence_proxy_async_smem();
+        if (issuer) ptx::bulk_wait_group_read0();  // (the buffer written next was read by the store one chunk ago)
+        ptx::named_bar_sync(1, kAttSoftThreads);
+        if (issuer) {
+          ptx::tma_store_3d(&tmO, obuf, head * HD + cc * 64, t0, b);
+          ptx::bulk_commit_group();
+        }
+      }
+      // the P buffers are rewritten by the next tile's softmax: the stores must have read them out
+      if (issuer) ptx::bulk_wait_group_read0();
+      ptx::named_bar_sync(1, kAttSoftThreads);
+    }
+    if (issuer) ptx::bulk_wait_group0();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int HD>
+static int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, float clip, cudaStream_t stream) {
+  using Cfg = AttCfg<HD>;
+  static bool attr = false;
+  if (!attr) {
+    AMT_CUDA(cudaFuncSetAttribute(attention_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr = true;
+  }
+  const int D = heads * HD;
+  CUtensorMap tq, tkv, to;
+  {
+    uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)T, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)3 * D * 2, (uint64_t)T * 3 * D * 2};
+    uint32_t boxq[3] = {64, kAttQ, 1}, boxk[3] = {64, kAttK, 1};
+    AMT_TRY(encode_tmap_bf16(&tq, qkv, 3, dims, str, boxq, CU_TENSOR_MAP_SWIZZLE_128B));
+    AMT_TRY(encode_tmap_bf16(&tkv, qkv, 3, dims, str, boxk, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)D, (uint64_t)T, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)D * 2, (uint64_t)T * D * 2};
+    uint32_t box[3] = {64, kAttQ, 1};
+    AMT_TRY(encode_tmap_bf16(&to, out, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  AttParams p;
+  p.T = T;
+  p.heads = heads;
+  p.B = B;
+  p.q_tiles = ceil_div(T, kAttQ);
+  const long long nt = static_cast<long long>(B) * heads * p.q_tiles;
+  AMT_REQUIRE(nt < (1ll << 31), "attention: too many tiles");
+  p.num_tiles = static_cast<int>(nt);
+  p.nb = ceil_div(T, kAttK);
+  p.D = D;
+  p.scale = 1.0f / sqrtf(static_cast<float>(HD));
+  p.clip = clip;
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  attention_tc_kernel<HD><<<grid, kAttThreads, Cfg::kSmemBytes, stream>>>(tq, tkv, to, p);
+  AMT_CHECK_LAUNCH();
+  return 0;
+}
+
+int run_attention_tc(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip, cudaStream_t stream) {
+  switch (head_dim) {
+    case 64: return launch_attention_tc<64>(qkv, out, B, T, heads, clip, stream);
+    case 128: return launch_attention_tc<128>(qkv, out, B, T, heads, clip, stream);
+    case 192: return launch_attention_tc<192>(qkv, out, B, T, heads, clip, stream);
+    default: return set_error(AMT_ERR_ARG, "attention (tcgen05): head_dim %d unsupported", head_dim);
+  }
+}
+
+}  // namespace amt

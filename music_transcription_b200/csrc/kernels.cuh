@@ -13,6 +13,7 @@ int run_gemm(const void* A, const void* W, const float* bias, void* C, int M, in
 int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t lstm_scratch_bytes(const amt_lstm_seq* seqs, int n_seq, int B);
 int run_attention(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip, cudaStream_t stream);
+int run_attention_tc(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip, cudaStream_t stream);
 int run_conv1(const float* x, const float* w, const float* bias, void* out, int B, int Fin, int T, cudaStream_t stream);
 int run_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, void* out, long long rows,
                       int D, float eps, cudaStream_t stream);

@@ -172,7 +172,8 @@ def test_lstm_recurrence_matches_stepwise_reference(B, T, Hs):
 
 
 # ----------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("B,T,hd", [(1, 64, 48), (2, 100, 48), (1, 938, 192), (2, 77, 96), (1, 130, 144)])
+@pytest.mark.parametrize("B,T,hd", [(1, 64, 48), (2, 100, 48), (1, 938, 192), (2, 77, 96), (1, 130, 144),
+                                     (3, 300, 192), (2, 129, 64), (1, 500, 128), (20, 938, 192)])
 def test_attention_matches_clamped_softmax(B, T, hd):
     heads = 8
     D = heads * hd

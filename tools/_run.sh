@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-bash tools/gpu_tests.sh > gpurun_out/tests_o.log 2>&1; cat gpurun_out/summary.txt; grep -h "FAILED\|Error" gpurun_out/test_*.log | head
+timeout 300 python -m pytest tests/test_gpu_model.py -q -m gpu --timeout 120 2>&1 | tail -3
 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err; tail -c 300 gpurun_out/bench_b.err
 python - <<'PY'
 import json
