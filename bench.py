@@ -66,6 +66,16 @@ def stage_flops(B: int) -> dict:
     return {k: v * B for k, v in f.items()}
 
 
+def ncu_traffic(stage: str, chunks: int):
+    """DRAM bytes of one launch of `stage` from the committed ncu --set full capture (same chunk count only)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic_chunks64.json")
+    try:
+        d = json.load(open(p))
+        return d["dram_bytes_per_launch"].get(stage) if d.get("chunks") == chunks else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -315,10 +325,15 @@ def main():
         top = gemm_like[0] if gemm_like else None
         roofline = None
         if top:
-            roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05/TMA implicit GEMM) stage " + top["stage"],
+            st = top["stage"]
+            kern = ("conv_halo_kernel (tcgen05/TMA halo-tile implicit-GEMM conv)" if st.startswith(("res", "freq", "c2"))
+                    else "attention_tc_kernel (tcgen05 fused clamped-softmax attention)" if st == "attn.core"
+                    else "tc_gemm_kernel (tcgen05/TMA persistent GEMM)")
+            roofline = {"bound": "tensor", "kernel": f"{kern}, stage {st}",
                         "achieved": top["tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": round(top["tflops"] / tf_peak, 4),
-                        "traffic": None, "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
-                        "algorithmic_flops_per_launch": fl[top["stage"]], "ms_per_launch": top["ms_per_launch"]}
+                        "traffic": ncu_traffic(st, C), "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
+                        "algorithmic_flops_per_launch": fl[st], "ms_per_launch": top["ms_per_launch"],
+                        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that launch, profiles/r1_traffic_chunks64.json"}
         total_flops = sum(stage_flops(C).values())
         line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 1), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
