@@ -307,6 +307,7 @@ static int lstm_plan(const amt_lstm_seq* seqs, int n_seq, int B, LstmPlan* plan)
 // clusters are co-scheduled by hardware and independent of each other.
 // ============================================================================
 constexpr int kMaxClusterCtas = 64;     // CTAs of one batch group (all its clusters)
+constexpr int kHGroups = 1;             // barriers per h buffer: sender slices are split into this many groups
 constexpr int kWCol0 = 64;              // TMEM columns [0,64): accumulator D; [64, 64 + H/2): W_hh slice
 constexpr int kTmemColsCluster = 512;
 
@@ -353,14 +354,13 @@ lstm_cluster_kernel(const LstmClusterParams p) {
   uint8_t* stage = h_smem + 2 * hbuf_bytes;                       // 2 x kSliceBytes: this slice's new h (pre-swizzled)
   float* xch = reinterpret_cast<float*>(stage + 2 * kSliceBytes); // [16 warps][32][XP]
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(xch + 16 * 32 * XP);
-  uint64_t* hbar = mma_bar + 1;                                   // [2]: h tile buffer complete (n_peers x kSliceBytes of complete_tx)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hbar + 2);
+  uint64_t* hbar = mma_bar + 1;                                   // [2 buffers][kHGroups]: those sender slices' blocks have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hbar + 2 * kHGroups);
 
   if (warp == 0) {
     if (lane == 0) {
       ptx::mbar_init(mma_bar, 1);
-      ptx::mbar_init(&hbar[0], 1);
-      ptx::mbar_init(&hbar[1], 1);
+      for (int i = 0; i < 2 * kHGroups; ++i) ptx::mbar_init(&hbar[i], 1);
       ptx::mbar_fence_init();
     }
     __syncwarp();
@@ -410,11 +410,14 @@ lstm_cluster_kernel(const LstmClusterParams p) {
     const bool mma_leader = ptx::elect_one_sync();
     const uint32_t w_tmem = tmem_base + kWCol0;    // A operand: 8 columns (16 bf16) per MMA
     const uint64_t h_desc0 = ptx::umma_desc_sw64(ptx::smem_u32(h_smem));
-    // lane l < n_peers of warp 15 delivers this slice's block to peer l: shared::cluster addresses of the
-    // peer's block `slice` (buffer 0) and of its hbar[0]
-    const uint32_t peer_rank = static_cast<uint32_t>(peer0 + (lane < n_peers ? lane : 0));
+    // Lane 0 of warp w < n_peers delivers this slice's block to slice (slice + w) % n_peers: 16 different
+    // warps issue the 16 bulk copies in parallel (one lane looping over them costs ~90 cycles per copy,
+    // which -- not the DSMEM bandwidth -- was the length of the exchange).  shared::cluster addresses of
+    // the peer's block `slice` (buffer 0) and of the barrier of this slice's group in its hbar[0].
+    const int per_group = n_peers / kHGroups;
+    const uint32_t peer_rank = static_cast<uint32_t>(peer0 + (warp < n_peers ? (slice + warp) % n_peers : 0));
     const uint32_t peer_dst = ptx::mapa(ptx::smem_u32(h_smem + slice * kSliceBytes), peer_rank);
-    const uint32_t peer_bar = ptx::mapa(ptx::smem_u32(hbar), peer_rank);
+    const uint32_t peer_bar = ptx::mapa(ptx::smem_u32(&hbar[slice / per_group]), peer_rank);
     // this thread's cell (unit ul, chunk b) in the pre-swizzled staging block: row b, 16-byte chunk ul/8
     auto stage_off = [&](int b) { return b * 64 + ((((ul >> 3) ^ (b >> 1)) & 3) << 4) + (ul & 7) * 2; };
 
@@ -474,21 +477,25 @@ lstm_cluster_kernel(const LstmClusterParams p) {
 
       if (step > 0) {
         const int buf = (step - 1) & 1;
-        ptx::mbar_wait(&hbar[buf], ((step - 1) >> 1) & 1);     // all K blocks of h_{t-1} have landed (TMA complete_tx)
-        TRACE_MARK(0);
         store_outputs(sq.reverse ? t + 1 : t - 1);
         if (warp == 0) {
-          ptx::tc_fence_after();
-          if (mma_leader) {
-            const uint64_t hd = h_desc0 + static_cast<uint64_t>((buf * hbuf_bytes) >> 4);
-            for (int sb = 0; sb < n_peers; ++sb) {           // one 32-unit block per slice, two K=16 MMAs each
+          const uint64_t hd = h_desc0 + static_cast<uint64_t>((buf * hbuf_bytes) >> 4);
+          const uint32_t hpar = ((step - 1) >> 1) & 1;
+          for (int gi = 0; gi < kHGroups; ++gi) {
+            ptx::mbar_wait(&hbar[buf * kHGroups + gi], hpar);      // the blocks of this group of slices have landed
+            if (gi == 0) TRACE_MARK(0);
+            ptx::tc_fence_after();
+            if (mma_leader) {
+              for (int sb = gi * per_group; sb < (gi + 1) * per_group; ++sb) {   // one 32-unit block per slice, two K=16 MMAs
 #pragma unroll
-              for (int k = 0; k < 2; ++k)
-                ptx::umma_bf16_ts(tmem_base, w_tmem + static_cast<uint32_t>(sb * 16 + k * 8),
-                                  hd + static_cast<uint64_t>(sb * (kSliceBytes >> 4) + 2 * k), idesc, (sb | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 2; ++k)
+                  ptx::umma_bf16_ts(tmem_base, w_tmem + static_cast<uint32_t>(sb * 16 + k * 8),
+                                    hd + static_cast<uint64_t>(sb * (kSliceBytes >> 4) + 2 * k), idesc, (sb | k) != 0 ? 1u : 0u);
+              }
             }
-            ptx::umma_commit(mma_bar);
+            __syncwarp();
           }
+          if (mma_leader) ptx::umma_commit(mma_bar);
           __syncwarp();
         }
         ptx::mbar_wait(mma_bar, parity);
@@ -536,11 +543,12 @@ lstm_cluster_kernel(const LstmClusterParams p) {
         const int chunk = pc ^ ((pb >> 1) & 3);
         pub_val = *reinterpret_cast<const uint4*>(stage_t + pb * 64 + chunk * 16);
       }
-      if (step + 1 < p.T && warp == 15) {
+      if (step + 1 < p.T && lane == 0) {
         const int buf = step & 1;
-        if (lane == 0) ptx::mbar_expect_tx(&hbar[buf], static_cast<uint32_t>(hbuf_bytes));
-        if (lane < n_peers)
-          ptx::bulk_copy_to_peer(peer_dst + buf * hbuf_bytes, ptx::smem_u32(stage_t), kSliceBytes, peer_bar + buf * 8);
+        if (warp < kHGroups) ptx::mbar_expect_tx(&hbar[buf * kHGroups + warp], static_cast<uint32_t>(per_group * kSliceBytes));
+        if (warp < n_peers)
+          ptx::bulk_copy_to_peer(peer_dst + buf * hbuf_bytes, ptx::smem_u32(stage_t), kSliceBytes,
+                                 peer_bar + buf * (kHGroups * 8));
       }
       TRACE_MARK(3);
     }
@@ -560,7 +568,7 @@ lstm_cluster_kernel(const LstmClusterParams p) {
 
 static size_t lstm_cluster_smem_bytes(int Hmax, int BC) {
   return 2 * static_cast<size_t>(Hmax / 32) * BC * 64 + 2 * static_cast<size_t>(BC) * 64 +
-         16 * 32 * (BC / 4 + 1) * 4 + 64 + 1024;
+         16 * 32 * (BC / 4 + 1) * 4 + 320 + 1024;
 }
 
 struct ClusterPlan {
@@ -745,7 +753,7 @@ int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, s
       AMT_CUDA(cudaStreamSynchronize(stream));
       AMT_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
       cudaFree(trace_dev);
-      fprintf(stderr, "[lstm cluster trace] n_seq=%d BC=%d CS=%d grid=%d T=%d cycles/step: h-wait %.0f out-stores+mma %.0f epilogue %.0f publish %.0f\n",
+      fprintf(stderr, "[lstm cluster trace] n_seq=%d BC=%d CS=%d grid=%d T=%d cycles/step: h-wait %.0f mma %.0f epilogue %.0f publish %.0f\n",
               n_seq, cp.BC, cp.CS, grid, T, (double)h[0] / T, (double)h[1] / T, (double)h[2] / T, (double)h[3] / T);
     }
     return 0;
