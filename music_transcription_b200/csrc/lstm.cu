@@ -307,7 +307,6 @@ static int lstm_plan(const amt_lstm_seq* seqs, int n_seq, int B, LstmPlan* plan)
 // clusters are co-scheduled by hardware and independent of each other.
 // ============================================================================
 constexpr int kMaxClusterCtas = 64;     // CTAs of one batch group (all its clusters)
-constexpr int kHGroups = 1;             // barriers per h buffer: sender slices are split into this many groups
 constexpr int kWCol0 = 64;              // TMEM columns [0,64): accumulator D; [64, 64 + H/2): W_hh slice
 constexpr int kTmemColsCluster = 512;
 
@@ -327,6 +326,7 @@ lstm_cluster_kernel(const LstmClusterParams p) {
   constexpr int NC = BC / 4;
   constexpr int XP = NC + 1;
   constexpr int kSliceBytes = BC * 64;             // one slice's h_t: BC rows x 32 units bf16, SWIZZLE_64B rows
+  constexpr int kHalfBytes = kSliceBytes / 2;      // the BC/2 chunk rows one CTA of a pair keeps (cta_group::2 splits B along N)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -342,30 +342,39 @@ lstm_cluster_kernel(const LstmClusterParams p) {
   const int peer0 = p.cta_peer0[within];
   const int H = sq.H;
   const int n_peers = sq.n_slices;
-  const int hbuf_bytes = n_peers * kSliceBytes;
+  const int hbuf_bytes = n_peers * kHalfBytes;
+  const bool pair_leader = (slice & 1) == 0;       // even slice = leader CTA of the pair (cluster ranks 2i, 2i+1)
 
+  // CTA PAIRS: slices 2i and 2i+1 run ONE tcgen05.mma.cta_group::2 per K step (M = 256: 128 gate rows
+  // from each CTA's tensor memory); the B operand h_{t-1} is split along N between the two CTAs, so each
+  // CTA keeps -- and RECEIVES -- only BC/2 of the BC chunk rows.  The per-step all-to-all of h is bound by
+  // the ~17 B/clk/SM DSMEM bandwidth, so halving the bytes per CTA halves the longest phase of the step.
   // W_hh slice lives in TENSOR MEMORY (A operand of tcgen05.mma, TS form): lane = gate row, 32-bit
   // column j of the W region = (W[row][2j], W[row][2j+1]).  The MMA then reads only the small h tile
   // from shared memory (the SS form re-reads the 128 KB slice every step: ~1000 smem-bound cycles).
-  // B operand: h_{t-1} as n_peers blocks of [BC rows][32 units] (64-byte rows, SWIZZLE_64B), block s
-  // written by slice s -- each block is ONE contiguous 2 KB region, so a peer delivers it with a single
-  // bulk DSMEM copy.
+  // B operand: h_{t-1} as n_peers blocks of [BC/2 rows][32 units] (64-byte rows, SWIZZLE_64B), block s
+  // written by slice s -- each block is ONE contiguous region, so a peer delivers it with a single
+  // bulk DSMEM copy (rows 0..BC/2-1 of its staging block to the even CTAs, the rest to the odd ones).
   uint8_t* h_smem = smem;                                         // 2 x hbuf_bytes, double buffered
   uint8_t* stage = h_smem + 2 * hbuf_bytes;                       // 2 x kSliceBytes: this slice's new h (pre-swizzled)
   float* xch = reinterpret_cast<float*>(stage + 2 * kSliceBytes); // [16 warps][32][XP]
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(xch + 16 * 32 * XP);
-  uint64_t* hbar = mma_bar + 1;                                   // [2 buffers][kHGroups]: those sender slices' blocks have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hbar + 2 * kHGroups);
+  uint64_t* hbar = mma_bar + 1;                                   // [2 buffers]: this CTA's half of h has landed
+  uint64_t* pair_bar = hbar + 2;                                  // [2 buffers] (leader): the odd CTA's half has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pair_bar + 2);
 
   if (warp == 0) {
     if (lane == 0) {
       ptx::mbar_init(mma_bar, 1);
-      for (int i = 0; i < 2 * kHGroups; ++i) ptx::mbar_init(&hbar[i], 1);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&hbar[i], 1);
+        ptx::mbar_init(&pair_bar[i], 1);
+      }
       ptx::mbar_fence_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, kTmemColsCluster);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc_pair(tmem_slot, kTmemColsCluster);     // both CTAs of the pair, same warp, same smem slot
+    ptx::tmem_relinquish_pair();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -406,18 +415,21 @@ lstm_cluster_kernel(const LstmClusterParams p) {
     const float act_c = gate == 2 ? 0.0f : 0.5f;
     const float* gx_row = sq.gx + slice * 128 + r;
     float* xw = xch + warp * 32 * XP;
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BC);
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, BC);     // the pair's 256 gate rows x BC chunks
     const bool mma_leader = ptx::elect_one_sync();
     const uint32_t w_tmem = tmem_base + kWCol0;    // A operand: 8 columns (16 bf16) per MMA
     const uint64_t h_desc0 = ptx::umma_desc_sw64(ptx::smem_u32(h_smem));
-    // Lane 0 of warp w < n_peers delivers this slice's block to slice (slice + w) % n_peers: 16 different
-    // warps issue the 16 bulk copies in parallel (one lane looping over them costs ~90 cycles per copy,
-    // which -- not the DSMEM bandwidth -- was the length of the exchange).  shared::cluster addresses of
-    // the peer's block `slice` (buffer 0) and of the barrier of this slice's group in its hbar[0].
-    const int per_group = n_peers / kHGroups;
-    const uint32_t peer_rank = static_cast<uint32_t>(peer0 + (warp < n_peers ? (slice + warp) % n_peers : 0));
-    const uint32_t peer_dst = ptx::mapa(ptx::smem_u32(h_smem + slice * kSliceBytes), peer_rank);
-    const uint32_t peer_bar = ptx::mapa(ptx::smem_u32(&hbar[slice / per_group]), peer_rank);
+    // Lane 0 of warp w < n_peers delivers one half of this slice's block to slice (slice + w) % n_peers
+    // (rows 0..BC/2-1 to an even slice, the rest to an odd one): 16 different warps issue the 16 bulk
+    // copies in parallel.  shared::cluster addresses of the peer's block `slice` (buffer 0) and its hbar[0].
+    const int peer_slice = warp < n_peers ? (slice + warp) % n_peers : 0;
+    const uint32_t peer_rank = static_cast<uint32_t>(peer0 + peer_slice);
+    const uint32_t peer_dst = ptx::mapa(ptx::smem_u32(h_smem + slice * kHalfBytes), peer_rank);
+    const uint32_t peer_bar = ptx::mapa(ptx::smem_u32(hbar), peer_rank);
+    const uint32_t peer_src_off = static_cast<uint32_t>((peer_slice & 1) * kHalfBytes);
+    // odd CTA -> leader: "my half of h has landed";  leader -> both: MMAs of the step retired
+    const uint32_t leader_pair_bar = ptx::mapa(ptx::smem_u32(pair_bar), static_cast<uint32_t>(peer0 + (slice & ~1)));
+    const uint16_t pair_mask = static_cast<uint16_t>(3u << (peer0 + (slice & ~1)));
     // this thread's cell (unit ul, chunk b) in the pre-swizzled staging block: row b, 16-byte chunk ul/8
     auto stage_off = [&](int b) { return b * 64 + ((((ul >> 3) ^ (b >> 1)) & 3) << 4) + (ul & 7) * 2; };
 
@@ -481,21 +493,23 @@ lstm_cluster_kernel(const LstmClusterParams p) {
         if (warp == 0) {
           const uint64_t hd = h_desc0 + static_cast<uint64_t>((buf * hbuf_bytes) >> 4);
           const uint32_t hpar = ((step - 1) >> 1) & 1;
-          for (int gi = 0; gi < kHGroups; ++gi) {
-            ptx::mbar_wait(&hbar[buf * kHGroups + gi], hpar);      // the blocks of this group of slices have landed
-            if (gi == 0) TRACE_MARK(0);
+          ptx::mbar_wait(&hbar[buf], hpar);                  // this CTA's half of h_{t-1} has landed
+          if (!pair_leader) {
+            if (lane == 0) ptx::mbar_arrive_remote_relaxed(leader_pair_bar + buf * 8);
+          } else {
+            ptx::mbar_wait(&pair_bar[buf], hpar);            // ... and so has the odd CTA's half
+            TRACE_MARK(0);
             ptx::tc_fence_after();
             if (mma_leader) {
-              for (int sb = gi * per_group; sb < (gi + 1) * per_group; ++sb) {   // one 32-unit block per slice, two K=16 MMAs
+              for (int sb = 0; sb < n_peers; ++sb) {         // one 32-unit block per slice, two K=16 MMAs each
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
-                  ptx::umma_bf16_ts(tmem_base, w_tmem + static_cast<uint32_t>(sb * 16 + k * 8),
-                                    hd + static_cast<uint64_t>(sb * (kSliceBytes >> 4) + 2 * k), idesc, (sb | k) != 0 ? 1u : 0u);
+                  ptx::umma_bf16_ts_pair(tmem_base, w_tmem + static_cast<uint32_t>(sb * 16 + k * 8),
+                                         hd + static_cast<uint64_t>(sb * (kHalfBytes >> 4) + 2 * k), idesc, (sb | k) != 0 ? 1u : 0u);
               }
+              ptx::umma_commit_pair(mma_bar, pair_mask);     // arrives on mma_bar of BOTH CTAs
             }
-            __syncwarp();
           }
-          if (mma_leader) ptx::umma_commit(mma_bar);
           __syncwarp();
         }
         ptx::mbar_wait(mma_bar, parity);
@@ -545,10 +559,10 @@ lstm_cluster_kernel(const LstmClusterParams p) {
       }
       if (step + 1 < p.T && lane == 0) {
         const int buf = step & 1;
-        if (warp < kHGroups) ptx::mbar_expect_tx(&hbar[buf * kHGroups + warp], static_cast<uint32_t>(per_group * kSliceBytes));
+        if (warp == 15) ptx::mbar_expect_tx(&hbar[buf], static_cast<uint32_t>(hbuf_bytes));
         if (warp < n_peers)
-          ptx::bulk_copy_to_peer(peer_dst + buf * hbuf_bytes, ptx::smem_u32(stage_t), kSliceBytes,
-                                 peer_bar + buf * (kHGroups * 8));
+          ptx::bulk_copy_to_peer(peer_dst + buf * hbuf_bytes, ptx::smem_u32(stage_t) + peer_src_off, kHalfBytes,
+                                 peer_bar + buf * 8);
       }
       TRACE_MARK(3);
     }
@@ -559,16 +573,16 @@ lstm_cluster_kernel(const LstmClusterParams p) {
   }
 
   ptx::tc_fence_before();
-  ptx::cluster_sync_all();             // no CTA exits while a peer's multicast may still target its smem
+  ptx::cluster_sync_all();             // no CTA exits while a peer may still write its smem / use its TMEM
   if (warp == 0) {
     __syncwarp();
-    ptx::tmem_dealloc(tmem_base, kTmemColsCluster);
+    ptx::tmem_dealloc_pair(tmem_base, kTmemColsCluster);
   }
 }
 
 static size_t lstm_cluster_smem_bytes(int Hmax, int BC) {
-  return 2 * static_cast<size_t>(Hmax / 32) * BC * 64 + 2 * static_cast<size_t>(BC) * 64 +
-         16 * 32 * (BC / 4 + 1) * 4 + 320 + 1024;
+  return 2 * static_cast<size_t>(Hmax / 32) * (BC / 2) * 64 + 2 * static_cast<size_t>(BC) * 64 +
+         16 * 32 * (BC / 4 + 1) * 4 + 128 + 1024;
 }
 
 struct ClusterPlan {
