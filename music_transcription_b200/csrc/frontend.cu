@@ -73,7 +73,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples, int T, FrontendDev fe,
-              float* __restrict__ out, float* __restrict__ chunk_max) {
+              float* __restrict__ out, float* __restrict__ chunk_max, int vec_ok) {
   extern __shared__ __align__(16) uint8_t smem_fe[];
   const int span = (kFramesPerCta - 1) * fe.hop + kNfft;            // samples shared by the CTA's frames
   float* s_x = reinterpret_cast<float*>(smem_fe);                   // [span]
@@ -87,10 +87,30 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
   const float* x = wav + static_cast<long long>(b) * wav_stride;
 
   // stage samples [t0*hop - 1024, ... + span) with zero padding outside [0, n_samples)
+  // (all loads of a thread are in flight at once: 16-byte cp.async with zero fill outside the chunk;
+  //  a load -> store loop serialises ~44 DRAM round trips per thread)
   const int start = t0 * fe.hop - kHalf;
-  for (int i = tid; i < span; i += blockDim.x) {
-    const int g = start + i;
-    s_x[i] = (g >= 0 && g < n_samples) ? __ldg(x + g) : 0.0f;
+  if (vec_ok) {
+    for (int i = tid * 4; i < span; i += blockDim.x * 4) {
+      const int g = start + i;                                 // multiple of 4; n_samples % 4 == 0
+      const bool ok = g >= 0 && g < n_samples;
+      const int sz = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(s_x + i)), "l"(x + (ok ? g : 0)), "r"(sz)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  } else {
+    for (int i0 = tid; i0 < span; i0 += blockDim.x * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int g = start + i0 + u * blockDim.x;
+        v[u] = (i0 + u * blockDim.x < span && g >= 0 && g < n_samples) ? __ldg(x + g) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * blockDim.x < span) s_x[i0 + u * blockDim.x] = v[u];
+    }
   }
   __syncthreads();
 
@@ -333,7 +353,10 @@ int amt_logmel_f32(amt_frontend* fe, const float* wav, int B, int n_samples, int
   AMT_CHECK_LAUNCH();
   dim3 grid(ceil_div(T, kFramesPerCta), B);
   AMT_REQUIRE(B <= 65535, "logmel: B must be <= 65535");
-  logmel_kernel<<<grid, kWarpsPerCta * 32, smem, stream>>>(wav, wav_stride, n_samples, T, fe->dev, out_db, chunk_max);
+  // 16-byte staging needs aligned rows and a span that is a whole number of float4
+  const int vec_ok = (reinterpret_cast<uintptr_t>(wav) % 16 == 0) && (wav_stride % 4 == 0) && (n_samples % 4 == 0) &&
+                     (fe->hop % 4 == 0);
+  logmel_kernel<<<grid, kWarpsPerCta * 32, smem, stream>>>(wav, wav_stride, n_samples, T, fe->dev, out_db, chunk_max, vec_ok);
   AMT_CHECK_LAUNCH();
   if (top_db >= 0.0f) {
     const long long per_chunk = static_cast<long long>(fe->n_mels) * T;

@@ -692,6 +692,7 @@ static int lstm_cluster_plan(const amt_lstm_seq* seqs, int n_seq, int B, Cluster
     else if (cand == 32) AMT_TRY(lstm_cluster_max_active<32>(CS, smem, &max_active));
     else AMT_TRY(lstm_cluster_max_active<64>(CS, smem, &max_active));
     if (max_active < 1) break;
+    if (getenv("AMT_LSTM_TRACE")) fprintf(stderr, "[lstm plan] BC=%d CS=%d clusters/group=%d max_active_clusters=%d\n", cand, CS, clusters_per_group, max_active);
     BC = cand;
     if (ceil_div(B, cand) * clusters_per_group <= max_active) break;   // everything co-resident
   }
