@@ -4,91 +4,113 @@
 //     (main.py:164-186) so seam-crossing notes merge exactly as in the reference;
 //   * framewise TP/FP/FN for a whole threshold grid in ONE pass over the data
 //     (reference scripts/evaluate.py:524-553 re-runs the model per threshold).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace amt {
 
+// The roll is the VIRTUAL concatenation of n_seg per-chunk rolls (main.py:164-186): frame tt of pitch p
+// lives in segment tt / T at offset tt % T.  One warp owns one (pitch, segment): 88 x n_seg warps scan
+// the roll in parallel (a CTA per pitch walked 60 000 frames serially); a tiny scan kernel turns the
+// per-warp onset / offset counts into output ranks, so the note list comes out pitch-major and
+// onset-ascending exactly as the reference loop emits it (main.py:204-223).
 struct RollView {
   const float* vals;
   int n_seg, T;
   long long seg_stride, pitch_stride;
   float thr;
-  __device__ __forceinline__ bool active(int p, long long tt, long long total) const {
-    if (tt < 0 || tt >= total) return false;
-    const int seg = static_cast<int>(tt / T);
-    const int t = static_cast<int>(tt - static_cast<long long>(seg) * T);
-    return __ldg(vals + seg * seg_stride + p * pitch_stride + t) > thr;
+  // frame t of segment s, where t may be -1 (last frame of the previous segment) or T (first of the next)
+  __device__ __forceinline__ bool active(int p, int s, int t) const {
+    if (t < 0) { --s; t = T - 1; }
+    else if (t >= T) { ++s; t = 0; }
+    if (s < 0 || s >= n_seg) return false;
+    return __ldg(vals + s * seg_stride + p * pitch_stride + t) > thr;
   }
 };
 
-__global__ void __launch_bounds__(256) notes_count_kernel(RollView rv, int32_t* __restrict__ counts) {
-  const int p = blockIdx.x;
-  const long long total = static_cast<long long>(rv.n_seg) * rv.T;
-  int local = 0;
-  for (long long tt = threadIdx.x; tt < total; tt += 256)
-    local += (rv.active(p, tt, total) && !rv.active(p, tt - 1, total)) ? 1 : 0;
-  __shared__ int wsum[8];
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int s = 0;
-    for (int i = 0; i < 8; ++i) s += wsum[i];
-    counts[p] = s;
+// pass 1 (EMIT = false): onset / offset counts of every (pitch, segment);  pass 3 (EMIT = true): write the
+// onset frames and offset frames at their ranks.  A note is (pitch, first active frame, last active frame + 1).
+template <bool EMIT>
+__global__ void __launch_bounds__(256) notes_scan_kernel(RollView rv, int n_pitch, int32_t* __restrict__ cnt_on,
+                                                         int32_t* __restrict__ cnt_off, int32_t* __restrict__ notes, int cap) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= n_pitch * rv.n_seg) return;
+  const int p = w / rv.n_seg, s = w - p * rv.n_seg;
+  int on_run = EMIT ? cnt_on[w] : 0, off_run = EMIT ? cnt_off[w] : 0;      // EMIT: exclusive ranks from the scan
+  const unsigned lt = (1u << lane) - 1u;
+  for (int t0 = 0; t0 < rv.T; t0 += 32) {
+    const int t = t0 + lane;
+    const bool a = t < rv.T && rv.active(p, s, t);
+    const bool is_on = a && !rv.active(p, s, t - 1);
+    const bool is_off = a && !rv.active(p, s, t + 1);
+    const unsigned m_on = __ballot_sync(0xffffffffu, is_on), m_off = __ballot_sync(0xffffffffu, is_off);
+    if (EMIT) {
+      const int tt = s * rv.T + t;
+      if (is_on) {
+        const int idx = on_run + __popc(m_on & lt);
+        if (idx < cap) { notes[3 * idx + 0] = p; notes[3 * idx + 1] = tt; }
+      }
+      if (is_off) {
+        const int idx = off_run + __popc(m_off & lt);
+        if (idx < cap) notes[3 * idx + 2] = tt + 1;
+      }
+    }
+    on_run += __popc(m_on);
+    off_run += __popc(m_off);
   }
+  if (!EMIT && lane == 0) { cnt_on[w] = on_run; cnt_off[w] = off_run; }
 }
 
-__global__ void __launch_bounds__(256) notes_emit_kernel(RollView rv, const int32_t* __restrict__ counts_in,
-                                                         int32_t* __restrict__ counts_total, int n_pitch,
-                                                         int32_t* __restrict__ notes, int cap) {
-  const int p = blockIdx.x;
+// pass 2: in-place exclusive scan of both count arrays (pitch-major), per-pitch note counts and the total
+__global__ void __launch_bounds__(1024) notes_rank_kernel(int32_t* __restrict__ cnt_on, int32_t* __restrict__ cnt_off, int n,
+                                                          int n_seg, int n_pitch, int32_t* __restrict__ counts) {
+  __shared__ int wsum[2][32];
+  __shared__ int carry[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long total = static_cast<long long>(rv.n_seg) * rv.T;
-  __shared__ int s_base;
-  __shared__ int w_on[8], w_off[8];
-  if (warp == 0) {
-    int s = 0;
-    for (int i = lane; i < p; i += 32) s += counts_in[i];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) {
-      s_base = s;
-      if (p == n_pitch - 1) counts_total[0] = s + counts_in[p];
-    }
-  }
+  if (tid < 2) carry[tid] = 0;
   __syncthreads();
-  const int base = s_base;
-  int on_run = 0, off_run = 0;                 // block-uniform running ranks
-  for (long long c0 = 0; c0 < total; c0 += 256) {
-    const long long tt = c0 + tid;
-    const bool a = rv.active(p, tt, total);
-    const bool is_on = a && !rv.active(p, tt - 1, total);
-    const bool is_off = a && !rv.active(p, tt + 1, total);     // note ends after frame tt -> offset index tt + 1
-    const unsigned m_on = __ballot_sync(0xffffffffu, is_on), m_off = __ballot_sync(0xffffffffu, is_off);
-    if (lane == 0) { w_on[warp] = __popc(m_on); w_off[warp] = __popc(m_off); }
-    __syncthreads();
-    int pre_on = 0, pre_off = 0, tot_on = 0, tot_off = 0;
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + tid;
+    const int v0 = i < n ? cnt_on[i] : 0, v1 = i < n ? cnt_off[i] : 0;
+    int x0 = v0, x1 = v1;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      pre_on += i < warp ? w_on[i] : 0;
-      pre_off += i < warp ? w_off[i] : 0;
-      tot_on += w_on[i];
-      tot_off += w_off[i];
+    for (int off = 1; off < 32; off <<= 1) {
+      const int y0 = __shfl_up_sync(0xffffffffu, x0, off), y1 = __shfl_up_sync(0xffffffffu, x1, off);
+      if (lane >= off) { x0 += y0; x1 += y1; }
     }
-    const unsigned lt = (1u << lane) - 1u;
-    if (is_on) {
-      const int idx = base + on_run + pre_on + __popc(m_on & lt);
-      if (idx < cap) { notes[3 * idx + 0] = p; notes[3 * idx + 1] = static_cast<int32_t>(tt); }
+    if (lane == 31) { wsum[0][warp] = x0; wsum[1][warp] = x1; }
+    __syncthreads();
+    if (warp == 0) {
+      int a0 = wsum[0][lane], a1 = wsum[1][lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y0 = __shfl_up_sync(0xffffffffu, a0, off), y1 = __shfl_up_sync(0xffffffffu, a1, off);
+        if (lane >= off) { a0 += y0; a1 += y1; }
+      }
+      wsum[0][lane] = a0;
+      wsum[1][lane] = a1;
     }
-    if (is_off) {
-      const int idx = base + off_run + pre_off + __popc(m_off & lt);
-      if (idx < cap) notes[3 * idx + 2] = static_cast<int32_t>(tt + 1);
+    __syncthreads();
+    const int b0 = carry[0] + (warp > 0 ? wsum[0][warp - 1] : 0), b1 = carry[1] + (warp > 0 ? wsum[1][warp - 1] : 0);
+    if (i < n) {
+      const int e0 = b0 + x0 - v0;                          // exclusive rank of this (pitch, segment)
+      cnt_on[i] = e0;
+      cnt_off[i] = b1 + x1 - v1;
+      if (i % n_seg == 0) counts[i / n_seg] = e0;           // start rank of the pitch (differenced below)
     }
-    on_run += tot_on;
-    off_run += tot_off;
+    __syncthreads();
+    if (tid == 0) { carry[0] += wsum[0][31]; carry[1] += wsum[1][31]; }
     __syncthreads();
   }
+  if (tid == 0) counts[n_pitch] = carry[0];
+  __syncthreads();
+  // start ranks -> per-pitch counts  (read all, then write: one CTA, so a barrier separates the phases)
+  int mine = 0;
+  if (tid < n_pitch) mine = counts[tid + 1] - counts[tid];
+  __syncthreads();
+  if (tid < n_pitch) counts[tid] = mine;
 }
 
 // ----------------------------------------------------------------------------
@@ -158,10 +180,31 @@ int amt_threshold_notes(const float* vals, int n_seg, int n_pitch, int T, int64_
   AMT_REQUIRE(n_seg >= 1 && n_pitch >= 1 && T >= 1 && cap >= 0, "threshold_notes: bad sizes");
   AMT_TRY(ensure_device());
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  AMT_REQUIRE(n_pitch <= 1024, "threshold_notes: at most 1024 pitches");
+  AMT_REQUIRE(static_cast<long long>(n_seg) * T < (1ll << 31), "threshold_notes: roll too long");
   RollView rv{vals, n_seg, T, seg_stride, pitch_stride, thr};
-  notes_count_kernel<<<n_pitch, 256, 0, stream>>>(rv, counts);
+  const int n = n_pitch * n_seg;
+  // per-(pitch, segment) onset / offset counts -> ranks.  Library-owned scratch, grown on demand and reused
+  // (stream-ordered within one stream; like the handles, not for concurrent calls from several host threads)
+  static int32_t* scratch = nullptr;
+  static size_t scratch_ints = 0;
+  if (scratch_ints < 2 * static_cast<size_t>(n)) {
+    if (scratch) {
+      AMT_CUDA(cudaDeviceSynchronize());
+      AMT_CUDA(cudaFree(scratch));
+      scratch = nullptr;
+      scratch_ints = 0;
+    }
+    const size_t want = std::max<size_t>(2 * static_cast<size_t>(n), 1 << 16);
+    AMT_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), sizeof(int32_t) * want));
+    scratch_ints = want;
+  }
+  const int grid = ceil_div(n, 8);
+  notes_scan_kernel<false><<<grid, 256, 0, stream>>>(rv, n_pitch, scratch, scratch + n, notes, cap);
   AMT_CHECK_LAUNCH();
-  notes_emit_kernel<<<n_pitch, 256, 0, stream>>>(rv, counts, counts + n_pitch, n_pitch, notes, cap);
+  notes_rank_kernel<<<1, 1024, 0, stream>>>(scratch, scratch + n, n, n_seg, n_pitch, counts);
+  AMT_CHECK_LAUNCH();
+  notes_scan_kernel<true><<<grid, 256, 0, stream>>>(rv, n_pitch, scratch, scratch + n, notes, cap);
   AMT_CHECK_LAUNCH();
   return 0;
 }
