@@ -6,9 +6,15 @@
 // attention block, shared_fc and the stacked frame|onset|offset heads.  (The convolutions have their
 // own halo-tile kernel, conv_halo.cu.)
 //
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 =
-// epilogue.  Tile = 128 (M) x BN (N), BLOCK_K = 64 bf16 = one 128-B swizzle atom, 4-6 smem stages,
-// double-buffered TMEM accumulator (the epilogue of tile i overlaps the MMAs of tile i+1).
+// CTA PAIRS (cluster of 2, tcgen05.mma.cta_group::2): one tile = 256 (M) x BN (N); each CTA of the pair
+// owns 128 rows of A and of the accumulator and loads only HALF of the weight tile (BN/2 rows) -- the
+// tensor cores of both SMs read each other's half, so L2->SMEM traffic and smem reads per MMA drop by a
+// third against two independent 128 x BN tiles (the single-CTA kernel was L2/smem-bandwidth bound at
+// ~1470 TFLOP/s).  BLOCK_K = 64 bf16 = one 128-B swizzle atom, 6 smem stages.
+// Roles (320 threads per CTA): warp 0 = TMA producer (both CTAs; all loads complete on the LEADER's
+// full barrier), warp 1 = MMA issuer (leader CTA only; commits multicast to both CTAs' barriers)
+// + TMEM alloc, warps 2..9 = epilogue (both CTAs, own 128 rows).  Double-buffered TMEM accumulator
+// (the epilogue of tile i overlaps the MMAs of tile i+1).
 // Epilogue: two warps per TMEM lane quarter; each 128-byte-wide column chunk of the tile is staged in
 // a swizzled shared-memory buffer (double buffered) and written by ONE TMA tensor store, which also
 // clips the rows beyond M -- the warps never issue global stores themselves.
@@ -35,7 +41,7 @@ __device__ __forceinline__ int decode_tile(const GemmParams& p, int tile, int& m
   return ng * p.group_n + (rem - m * gsize);
 }
 
-constexpr int kBlockM = 128;
+constexpr int kBlockM = 128;                     // rows per CTA; a pair's tile is 2 * kBlockM
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kGemmThreads = 320;
@@ -45,8 +51,8 @@ constexpr int kOutChunkBytes = 128 * 128;        // one staged chunk: 128 rows x
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
-  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStages = 6;
+  static constexpr int kBBytes = (BN / 2) * kBlockK * 2;      // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kOutChunkBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -70,6 +76,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();          // 0 = leader of the pair
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -84,17 +92,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&tfull[i], 1);
-        ptx::mbar_init(&tempty[i], 8);
+        ptx::mbar_init(&tempty[i], 16);                  // 8 epilogue warps of each CTA of the pair
       }
       ptx::mbar_fence_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish_pair();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  ptx::cluster_sync_all();                               // the peer's barriers exist before anything targets them
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -102,18 +111,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The whole warp runs the (warp-uniform) loop; only the issuing instructions are predicated on
     // one elected lane, so coordinates / addresses stay in uniform registers.
     const bool leader = ptx::elect_one_sync();
+    const uint32_t full0_leader = ptx::mapa(ptx::smem_u32(full), 0);      // stage s: + 8*s
     uint32_t s = 0, ph = 0;
     uint8_t* a_dst = smem;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
       int m;
-      const int n0 = decode_tile(p, tile, m) * BN;
-      const int m0 = m * kBlockM;
+      const int n0 = decode_tile(p, tile, m) * BN + static_cast<int>(rank) * (BN / 2);
+      const int m0 = m * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         ptx::mbar_wait(&empty[s], ph ^ 1);
         if (leader) {
-          ptx::mbar_expect_tx(&full[s], Cfg::kStageBytes);
-          ptx::tma_load_2d(a_dst, &tmA, &full[s], kb * kBlockK, m0);
-          ptx::tma_load_2d(a_dst + kABytes, &tmB, &full[s], kb * kBlockK, n0);
+          if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * Cfg::kStageBytes);   // both CTAs' bytes land on this barrier
+          ptx::tma_load_2d_pair(a_dst, &tmA, full0_leader + 8 * s, kb * kBlockK, m0);
+          ptx::tma_load_2d_pair(a_dst + kABytes, &tmB, full0_leader + 8 * s, kb * kBlockK, n0);
         }
         __syncwarp();
         a_dst += Cfg::kStageBytes;
@@ -125,39 +135,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    const bool leader = ptx::elect_one_sync();
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, BN);
-    const uint64_t desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smem));     // stage 0, A tile, k = 0
-    uint32_t s = 0, ph = 0, tl = 0;
-    uint64_t a_desc = desc0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
-      const uint32_t acc = tl & 1;
-      const uint32_t aph = (tl >> 1) & 1;
-      ptx::mbar_wait(&tempty[acc], aph ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        ptx::mbar_wait(&full[s], ph);
+    // ------------------------------ MMA issuer (leader CTA) --------------------
+    if (rank == 0) {
+      const bool leader = ptx::elect_one_sync();
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kBlockM, BN);
+      const uint64_t desc0 = ptx::umma_desc_sw128(ptx::smem_u32(smem));     // stage 0, A tile, k = 0
+      uint32_t s = 0, ph = 0, tl = 0;
+      uint64_t a_desc = desc0;
+      for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++tl) {
+        const uint32_t acc = tl & 1;
+        const uint32_t aph = (tl >> 1) & 1;
+        ptx::mbar_wait(&tempty[acc], aph ^ 1);
         ptx::tc_fence_after();
-        // descriptors differ only in the 14-bit start-address field (units of 16 bytes)
-        const uint64_t b_desc = a_desc + static_cast<uint64_t>(kABytes >> 4);
-        if (leader) {
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          // descriptors differ only in the 14-bit start-address field (units of 16 bytes)
+          const uint64_t b_desc = a_desc + static_cast<uint64_t>(kABytes >> 4);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          ptx::umma_commit(&empty[s]);   // frees the smem slot once these MMAs retire
+            for (int k = 0; k < kBlockK / 16; ++k)
+              ptx::umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_commit_pair(&empty[s], 3);   // frees the smem slot of BOTH CTAs once these MMAs retire
+          }
+          __syncwarp();
+          a_desc += static_cast<uint64_t>(Cfg::kStageBytes >> 4);
+          if (++s == Cfg::kStages) {
+            s = 0;
+            ph ^= 1;
+            a_desc = desc0;
+          }
         }
+        if (leader) ptx::umma_commit_pair(&tfull[acc], 3);   // accumulator ready for both epilogues
         __syncwarp();
-        a_desc += static_cast<uint64_t>(Cfg::kStageBytes >> 4);
-        if (++s == Cfg::kStages) {
-          s = 0;
-          ph ^= 1;
-          a_desc = desc0;
-        }
       }
-      if (leader) ptx::umma_commit(&tfull[acc]);   // accumulator ready for the epilogue
-      __syncwarp();
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
@@ -166,11 +178,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool issuer = threadIdx.x == kGemmEpiWarp0 * 32;
     const int r = q * 32 + lane;                     // tile row
     const uint32_t o_row = static_cast<uint32_t>(r) * 128u;
+    const uint32_t tempty0_leader = ptx::mapa(ptx::smem_u32(tempty), 0);
     uint32_t tl = 0, chunk_no = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++tl) {
       int m;
       const int n0 = decode_tile(p, tile, m) * BN;
-      const int m0 = m * kBlockM;
+      const int m0 = m * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
       const uint32_t acc = tl & 1;
       ptx::mbar_wait(&tfull[acc], (tl >> 1) & 1);
       ptx::tc_fence_after();
@@ -180,10 +193,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[kWarpCols];
         ptx::tmem_ld_cols<kWarpCols>(taddr + c * kChunkCols, v);
         ptx::tmem_ld_wait();
-        if (c == BN / kChunkCols - 1) {              // accumulator fully read: hand it back to the MMA warp
+        if (c == BN / kChunkCols - 1) {              // accumulator fully read: hand it back to the leader's MMA warp
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+          if (lane == 0) ptx::mbar_arrive_remote_relaxed(tempty0_leader + 8 * acc);
         }
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c * kChunkCols + half * kWarpCols);
         uint8_t* obuf = o_smem + (chunk_no & 1) * kOutChunkBytes;
@@ -234,11 +247,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   ptx::tc_fence_before();
   __syncthreads();
+  ptx::cluster_sync_all();                               // the leader's MMAs also wrote the peer's tensor memory
   if (warp == 1) {
     __syncwarp();
-    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
   }
 }
+
 
 // ----------------------------------------------------------------------------
 // host side
@@ -253,9 +268,21 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
-  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  tc_gemm_kernel<BN, OUT_F32><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, c, p);
-  AMT_CHECK_LAUNCH();
+  const int pairs = p.num_tiles < num_sms() / 2 ? p.num_tiles : num_sms() / 2;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AMT_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, OUT_F32>, a, b, c, p));
+  count_launch();
   return 0;
 }
 
@@ -281,7 +308,7 @@ int run_gemm(const void* A, const void* W, const float* bias, void* C, int M, in
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t str[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {64, (uint32_t)BN};
+    uint32_t box[2] = {64, (uint32_t)(BN / 2)};      // each CTA of a pair loads half of the weight tile
     AMT_TRY(encode_tmap_bf16(&bm, W, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   {
@@ -295,7 +322,7 @@ int run_gemm(const void* A, const void* W, const float* bias, void* C, int M, in
   GemmParams p;
   p.kblocks = K / 64;
   p.n_tiles = N / BN;
-  p.m_tiles = ceil_div(M, kBlockM);
+  p.m_tiles = ceil_div(M, 2 * kBlockM);
   p.group_n = p.n_tiles > 8 ? 8 : p.n_tiles;
   const long long nt = static_cast<long long>(p.m_tiles) * p.n_tiles;
   AMT_REQUIRE(nt < (1ll << 31), "gemm: too many tiles");
