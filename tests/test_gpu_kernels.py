@@ -33,6 +33,8 @@ def _bf(x):
     (938 * 2, 512, 1024, 1, 0),
     (300, 384, 1536, 0, 1),
     (4100, 1536, 640, 0, 0),
+    (129, 192, 64, 0, 0),            # second CTA of the pair owns a single valid row
+    (60032, 512, 256, 0, 0),         # config-[2]/[3] row count (64 x 938): 234.5 pair tiles
 ])
 def test_gemm_tcgen05_matches_fp32_matmul(M, N, K, relu, f32):
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
@@ -128,7 +130,9 @@ def _lstm_ref(gx, whh, reverse):
     return out
 
 
-@pytest.mark.parametrize("B,T,Hs", [(3, 12, (128,)), (16, 40, (128, 128, 64, 64)), (20, 25, (256, 256)), (5, 30, (512, 512, 256, 256))])
+@pytest.mark.parametrize("B,T,Hs", [(3, 12, (128,)), (16, 40, (128, 128, 64, 64)), (20, 25, (256, 256)), (5, 30, (512, 512, 256, 256)),
+                                    (40, 30, (512, 512)),                    # two batch groups of 32 chunks
+                                    (100, 20, (512, 512, 256, 256))])        # more chunks than co-resident clusters at 32: BC = 64
 def test_lstm_recurrence_matches_stepwise_reference(B, T, Hs):
     g = torch.Generator().manual_seed(B * 100 + T)
     L = _lib.lib()

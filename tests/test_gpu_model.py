@@ -184,3 +184,28 @@ def test_transcribe_chunks_end_to_end_notes_match_oracle_on_same_probs():
     assert np.array_equal(notes, want)
     nl = pipeline.pianoroll_to_midi(onotes.combine_piano_rolls(rolls), fs=16000 / 512)
     assert len(nl) == len(want) and all(n.velocity == 100 for n in nl.instruments[0].notes)
+
+
+def test_two_hour_recording_240_chunks_batch_invariance_and_notes():
+    """BASELINE configs[3] shape: 240 x 30-s chunks (full T = 938).  The oracle cannot run at this size, so the
+    test uses size-independent properties: (i) the note list does not depend on how the chunks are batched
+    (240 at once vs 64 + 64 + 64 + 48), (ii) it equals the oracle's grouping of the SAME GPU probability roll,
+    seams included, (iii) per-chunk logits are bitwise independent of the batch position."""
+    from oracle import notes as onotes
+    sd = synth.synth_state_dict("cnn_rnn", 320, 128, 1, seed=4, gain=2.0)
+    m = TranscriptionModel("cnn_rnn", n_mels=320, hidden_size=128, num_layers=1, device=DEV)
+    m.load_state_dict(sd)
+    base = synth.cheap_wave_batch(8, 480000, seed=7)
+    wav = torch.empty(240, 480000, device=DEV)
+    for i in range(240):
+        wav[i] = base[i % 8].to(DEV) * (1.0 - 0.003 * (i // 8))
+    notes_a, probs = pipeline.transcribe_chunks(m, wav, threshold=0.5, batch=240, return_probs=True)
+    notes_b, _ = pipeline.transcribe_chunks(m, wav, threshold=0.5, batch=64)
+    assert np.array_equal(notes_a, notes_b)
+    p = probs.cpu().numpy()
+    want = onotes.group_notes(onotes.combine_piano_rolls([onotes.threshold_roll(p[i], 0.5) for i in range(240)]))
+    assert np.array_equal(notes_a, want)
+    fe = pipeline.Frontend.get(device=DEV)
+    solo = m(fe.logmel(wav[100:101]))
+    batch = m(fe.logmel(wav[96:112]))
+    assert torch.equal(solo[0], batch[4])
