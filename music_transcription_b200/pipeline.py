@@ -141,6 +141,11 @@ class NoteList:
     def __len__(self):
         return len(self.triples)
 
+    def write(self, path: str) -> None:
+        """``pretty_midi.PrettyMIDI.write`` for this object (main.py:284): a format-1 Standard MIDI File."""
+        from . import smf
+        smf.write_smf(path, self.instruments[0].notes, self.instruments[0].program)
+
 
 def extract_notes(vals: torch.Tensor, threshold: float = 0.0, cap: int | None = None) -> np.ndarray:
     """Note grouping on the GPU.  ``vals`` is (88, T) or (n_seg, 88, T) CUDA float32 (probabilities
