@@ -2,7 +2,7 @@
 // called at reference main.py:117-125): centred zero-padded framing, periodic Hann,
 // real FFT, |X|^2, slaney mel projection, 10*log10, per-chunk (max - top_db) floor.
 //
-// One CTA = 4 warps handles 8 consecutive frames of one chunk.  The samples those
+// One CTA = 8 warps handles 8 consecutive frames of one chunk (one frame per warp).  The samples those
 // frames share (hop 512 / n_fft 2048 = 4x overlap) are staged once in shared memory
 // with coalesced loads; each warp then runs a 1024-point complex FFT of one real
 // 2048-sample frame entirely in registers + one shared-memory transpose
@@ -20,7 +20,7 @@ namespace amt {
 constexpr int kNfft = 2048;
 constexpr int kHalf = 1024;
 constexpr int kFramesPerCta = 8;
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 8;
 
 struct FrontendDev {
   const float* window;     // [2048] periodic Hann (fp64 -> fp32)
@@ -77,9 +77,8 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
   extern __shared__ __align__(16) uint8_t smem_fe[];
   const int span = (kFramesPerCta - 1) * fe.hop + kNfft;            // samples shared by the CTA's frames
   float* s_x = reinterpret_cast<float*>(smem_fe);                   // [span]
-  float2* s_z = reinterpret_cast<float2*>(s_x + ((span + 3) & ~3));  // [warps][32*33] transpose / spectrum
-  float* s_p = reinterpret_cast<float*>(s_z + kWarpsPerCta * 32 * 33);   // [warps][1028] power spectrum
-  float* s_out = s_p + kWarpsPerCta * 1028;                         // [n_mels][8]
+  float2* s_z = reinterpret_cast<float2*>(s_x + ((span + 3) & ~3));  // [warps][32*33] transpose / spectrum / power
+  float* s_out = reinterpret_cast<float*>(s_z + kWarpsPerCta * 32 * 33);   // [n_mels][8]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
@@ -115,7 +114,6 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
   __syncthreads();
 
   float2* zw = s_z + warp * 32 * 33;
-  float* pw = s_p + warp * 1028;
   float wmax = -INFINITY;
 
   for (int fi = warp; fi < kFramesPerCta; fi += kWarpsPerCta) {
@@ -147,22 +145,31 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
 #pragma unroll
       for (int sidx = 0; sidx < 32; ++sidx) zw[bitrev5(sidx) * 32 + lane] = v[sidx];   // natural order, k = k1 + 32*k2
       __syncwarp();
-      // real-FFT recovery: X[k] = E[k] + W_2048^k O[k],  k = 0..1024  (Z[1024] == Z[0])
-      for (int k = lane; k <= kHalf; k += 32) {
-        const float2 a = zw[k & 1023];
+      // real-FFT recovery in place.  With a = Z[k], c = Z[1024-k] (Z[1024] == Z[0]):
+      //   E = (a + conj c)/2,  O = (a - conj c)/(2i),  X[k] = E + W_2048^k O,  X[1024-k] = conj(E - W_2048^k O)
+      // so one pass over k = 0..512 yields both |X[k]|^2 and |X[1024-k]|^2; the pair is written back as
+      // float2 into slot k -- which only this lane reads (slot 1024-k, k <= 512, belongs to no other k).
+      for (int k = lane; k <= kHalf / 2; k += 32) {
+        const float2 a = zw[k];
         const float2 c = zw[(kHalf - k) & 1023];
         const float2 e = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
         const float2 o = make_float2(0.5f * (a.y + c.y), -0.5f * (a.x - c.x));   // (a - conj(c)) / (2i)
         const float2 w = __ldg(fe.tw2048 + k);
-        const float2 xk = make_float2(e.x + (o.x * w.x - o.y * w.y), e.y + (o.x * w.y + o.y * w.x));
-        pw[k] = xk.x * xk.x + xk.y * xk.y;
+        const float2 wo = make_float2(o.x * w.x - o.y * w.y, o.x * w.y + o.y * w.x);
+        const float px = e.x + wo.x, py = e.y + wo.y, qx = e.x - wo.x, qy = e.y - wo.y;
+        zw[k] = make_float2(px * px + py * py, qx * qx + qy * qy);     // (|X[k]|^2, |X[1024-k]|^2)
       }
       __syncwarp();
-      // banded mel projection + dB
+      // banded mel projection + dB.  power(j) = j <= 512 ? zw[j].x : zw[1024-j].y
+      const float* pf = reinterpret_cast<const float*>(zw);
       for (int m = lane; m < fe.n_mels; m += 32) {
         const int s = __ldg(fe.fb_start + m), o0 = __ldg(fe.fb_off + m), o1 = __ldg(fe.fb_off + m + 1);
         float acc = 0.0f;
-        for (int j = o0; j < o1; ++j) acc = fmaf(__ldg(fe.fb_w + j), pw[s + j - o0], acc);
+        for (int j = o0; j < o1; ++j) {
+          const int bin = s + j - o0;
+          const int idx = bin <= kHalf / 2 ? 2 * bin : 2 * (kHalf - bin) + 1;
+          acc = fmaf(__ldg(fe.fb_w + j), pf[idx], acc);
+        }
         const float db = 10.0f * log10f(fmaxf(acc, 1e-10f));
         s_out[m * kFramesPerCta + fi] = db;
         wmax = fmaxf(wmax, db);
@@ -343,7 +350,7 @@ int amt_logmel_f32(amt_frontend* fe, const float* wav, int B, int n_samples, int
   const int T = 1 + n_samples / fe->hop;
   const int span = (kFramesPerCta - 1) * fe->hop + kNfft;
   const size_t smem = sizeof(float) * ((span + 3) & ~3) + sizeof(float2) * kWarpsPerCta * 32 * 33 +
-                      sizeof(float) * kWarpsPerCta * 1028 + sizeof(float) * fe->n_mels * kFramesPerCta;
+                      sizeof(float) * fe->n_mels * kFramesPerCta;
   static size_t attr = 0;
   if (smem > attr) {
     AMT_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
