@@ -229,6 +229,41 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                 int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// Load into THIS CTA's smem, completing on the barrier at 32-bit shared address `bar_addr`: the CTA's own
+// (PAIR = false, a shared::cta address) or the pair leader's (PAIR = true, a shared::cluster address).
+template <bool PAIR>
+__device__ __forceinline__ void tma_load_2d_to(void* smem_dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1) {
+  if constexpr (PAIR) {
+    tma_load_2d_pair(smem_dst, m, bar_addr, c0, c1);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+template <bool PAIR>
+__device__ __forceinline__ void tma_load_4d_to(void* smem_dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1,
+                                               int c2, int c3) {
+  if constexpr (PAIR) {
+    tma_load_4d_pair(smem_dst, m, bar_addr, c0, c1, c2, c3);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
 // One box of a 3-D tensor, written to the same smem offset of every CTA in `cta_mask` of the cluster;
 // each destination CTA's mbarrier (same offset) receives the complete_tx.
 __device__ __forceinline__ void tma_load_3d_multicast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
@@ -343,6 +378,16 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (PAIR) umma_bf16_ss_pair(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
+  if constexpr (PAIR) umma_commit_pair(bar, 3);          // the barrier at this offset in both CTAs of the pair
+  else umma_commit(bar);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

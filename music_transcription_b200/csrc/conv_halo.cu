@@ -16,6 +16,9 @@
 // address, so a start address that is not a multiple of the swizzle atom reads exactly what TMA wrote.
 // L2->SMEM activation traffic drops from taps x 16 KB to 36 KB per tile and channel block.
 //
+// CTA pairs: the layers with 128 / 256 output channels run as clusters of 2 (tcgen05.mma.cta_group::2,
+// M = 256 = two adjacent tiles, one per CTA): each CTA loads its own halo tile but only HALF of every weight
+// block, which takes a third off the shared-memory traffic these layers are bound by.
 // Roles (352 threads): warp 0 = activation (A) producer, warp 1 = weight (B) producer, warp 2 = MMA
 // issuer (+ TMEM alloc), warps 3..10 = epilogue.  Two independent smem rings (A: halo tiles, B: one
 // [BN x KC] weight block per tap) and a double-buffered TMEM accumulator.
@@ -47,10 +50,12 @@ struct ConvHaloParams {
 
 template <int KC, int BN>
 struct ConvHaloCfg {
+  static constexpr bool kPair = BN >= 128;                             // CTA pairs (cta_group::2)
   static constexpr int kRowBytes = KC * 2;
   static constexpr int kABytes = kHaloF * kHaloT * kRowBytes;          // 36 KB (KC 64) / 18 KB (KC 32)
-  static constexpr int kBBytes = BN * kRowBytes;
-  static constexpr int kAStages = BN == 256 ? 2 : 3;
+  static constexpr int kBRows = kPair ? BN / 2 : BN;                   // weight rows this CTA loads per block
+  static constexpr int kBBytes = kBRows * kRowBytes;
+  static constexpr int kAStages = 3;
   static constexpr int kOutBytes = 2 * 128 * 128;                      // two staged [128 rows x 64 ch] output chunks
   static constexpr int kBudget = 225 * 1024 - kAStages * kABytes - kOutBytes - BN * 4 - 1024 - 512;
   static constexpr int kBStagesRaw = kBudget / kBBytes;
@@ -97,6 +102,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr bool PAIR = Cfg::kPair;
+  // work units: a tile (single CTA) or a pair of consecutive tiles (CTA pair; rank r takes tile 2u + r --
+  // a tile index past the end decodes to chunk == B: its loads are zero filled, its stores clipped)
+  const int rank = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int unit0 = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+  const int unit_step = PAIR ? gridDim.x >> 1 : gridDim.x;
+  const int num_units = PAIR ? (p.num_tiles + 1) >> 1 : p.num_tiles;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA0);
@@ -120,17 +132,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&tfull[i], 1);
-        ptx::mbar_init(&tempty[i], 8);
+        ptx::mbar_init(&tempty[i], PAIR ? 16 : 8);
       }
       ptx::mbar_fence_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish();
+    if constexpr (PAIR) {
+      ptx::tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  if constexpr (PAIR) ptx::cluster_sync_all();             // the peer's barriers exist before anything targets them
   const uint32_t tmem_base = *tmem_slot;
 
   constexpr int taps = KF * 3;
@@ -138,9 +156,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0) {
     // -------------------- activation producer: one halo box per channel block --------------------
     const bool leader = ptx::elect_one_sync();
+    const uint32_t afull0 = PAIR ? ptx::mapa(ptx::smem_u32(afull), 0) : ptx::smem_u32(afull);   // (the pair leader's)
+    constexpr uint32_t kShare = PAIR ? 2 : 1;              // CTAs whose bytes complete on one barrier
     uint32_t s = 0, ph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int m = tile;
+    for (int u = unit0; u < num_units; u += unit_step) {
+      int m = PAIR ? 2 * u + rank : u;
       const int f0 = (m % p.tilesF) * kTileF;
       m /= p.tilesF;
       const int t0 = (m % p.tilesT) * kTileT;
@@ -150,11 +170,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (leader) {
           uint8_t* dst = a_smem + s * Cfg::kABytes;
           if (e < p.cblks) {
-            ptx::mbar_expect_tx(&afull[s], Cfg::kABytes);
-            ptx::tma_load_4d(dst, &tmA0, &afull[s], e * KC, f0 - p.padF, t0 - p.padT, b);
+            if (rank == 0) ptx::mbar_expect_tx(&afull[s], kShare * Cfg::kABytes);
+            ptx::tma_load_4d_to<PAIR>(dst, &tmA0, afull0 + 8 * s, e * KC, f0 - p.padF, t0 - p.padT, b);
           } else {
-            ptx::mbar_expect_tx(&afull[s], static_cast<uint32_t>(kTileF * kTileT * p.kc2 * 2));
-            ptx::tma_load_4d(dst, &tmA1, &afull[s], (e - p.cblks) * p.kc2, f0, t0, b);
+            if (rank == 0) ptx::mbar_expect_tx(&afull[s], kShare * static_cast<uint32_t>(kTileF * kTileT * p.kc2 * 2));
+            ptx::tma_load_4d_to<PAIR>(dst, &tmA1, afull0 + 8 * s, (e - p.cblks) * p.kc2, f0, t0, b);
           }
         }
         __syncwarp();
@@ -167,16 +187,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else if (warp == 1) {
     // -------------------- weight producer: one [BN x KC] block per (channel block, tap) ----------
     const bool leader = ptx::elect_one_sync();
+    const uint32_t bfull0 = PAIR ? ptx::mapa(ptx::smem_u32(bfull), 0) : ptx::smem_u32(bfull);
+    constexpr uint32_t kShare = PAIR ? 2 : 1;
+    const int row0 = rank * Cfg::kBRows;                   // this CTA's half of the output channels
     uint32_t s = 0, ph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      if (p.resident && tile != static_cast<int>(blockIdx.x)) break;      // weights stay in smem after the first tile
+    for (int u = unit0; u < num_units; u += unit_step) {
+      if (p.resident && u != unit0) break;                 // weights stay in smem after the first tile
       for (int e = 0; e < p.cblks; ++e) {
         int col = e * KC;                       // weight column of (tap 0, block e); taps are cblks*KC apart
         for (int tap = 0; tap < taps; ++tap) {
           ptx::mbar_wait(&bempty[s], ph ^ 1);
           if (leader) {
-            ptx::mbar_expect_tx(&bfull[s], Cfg::kBBytes);
-            ptx::tma_load_2d(b_smem + s * Cfg::kBBytes, &tmB0, &bfull[s], col, 0);
+            if (rank == 0) ptx::mbar_expect_tx(&bfull[s], kShare * Cfg::kBBytes);
+            ptx::tma_load_2d_to<PAIR>(b_smem + s * Cfg::kBBytes, &tmB0, bfull0 + 8 * s, col, row0);
           }
           __syncwarp();
           col += p.cblks * KC;
@@ -189,8 +212,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int e = 0; e < p.cblks2; ++e) {
         ptx::mbar_wait(&bempty[s], ph ^ 1);
         if (leader) {
-          ptx::mbar_expect_tx(&bfull[s], static_cast<uint32_t>(BN * p.kc2 * 2));
-          ptx::tma_load_2d(b_smem + s * Cfg::kBBytes, &tmB1, &bfull[s], p.kmain + e * p.kc2, 0);
+          if (rank == 0) ptx::mbar_expect_tx(&bfull[s], kShare * static_cast<uint32_t>(Cfg::kBRows * p.kc2 * 2));
+          ptx::tma_load_2d_to<PAIR>(b_smem + s * Cfg::kBBytes, &tmB1, bfull0 + 8 * s, p.kmain + e * p.kc2, row0);
         }
         __syncwarp();
         if (++s == Cfg::kBStages) {
@@ -204,8 +227,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // The loop bodies are issue-bound for the small-N layers (a tap is only KC/16 MMAs of 32-64 tensor
     // cycles), so all per-tap state is carried incrementally and the filter loop is unrolled (kt == 3,
     // KF compile-time); with resident weights a tile is one straight-line burst of MMAs.
-    const bool leader = ptx::elect_one_sync();
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
+    const bool leader = ptx::elect_one_sync() && rank == 0;       // in a pair only the leader CTA issues
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(PAIR ? 256 : 128, BN);
     constexpr uint64_t kRow16 = Cfg::kRowBytes >> 4;            // one halo row, in descriptor address units
     constexpr uint64_t kBStage16 = Cfg::kBBytes >> 4;
     const uint32_t a_addr0 = ptx::smem_u32(a_smem), b_addr0 = ptx::smem_u32(b_smem);
@@ -217,7 +240,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint64_t b_skip0 = conv_desc(b_addr0, 8 * row2, row2);
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tl = 0;
     uint64_t a_stage = 0, b_stage = 0;                          // descriptor offsets of A stage sa / B stage sb
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+    for (int u = unit0; u < num_units && rank == 0; u += unit_step, ++tl) {
       const uint32_t acc = tl & 1;
       ptx::mbar_wait(&tempty[acc], ((tl >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
@@ -238,9 +261,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               for (int kti = 0; kti < 3; ++kti)
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k)
-                  ptx::umma_bf16_ss(d_tmem, a_tile + (kti * kHaloF + kfi) * kRow16 + 2 * k,
+                  ptx::umma_ss<PAIR>(d_tmem, a_tile + (kti * kHaloF + kfi) * kRow16 + 2 * k,
                                     b_desc + (kfi * 3 + kti) * kBStage16 + 2 * k, idesc, first | kfi | kti | k);
-            ptx::umma_commit(&aempty[sa]);
+            ptx::umma_commit_to<PAIR>(&aempty[sa]);
           }
           __syncwarp();
           first = 1;
@@ -258,8 +281,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           ptx::tc_fence_after();
           if (leader) {
             for (int k = 0; k < p.kc2 / 16; ++k)
-              ptx::umma_bf16_ss(d_tmem, a_skip0 + a_stage + 2 * k, b_skip + e * kBStage16 + 2 * k, idesc, first | k);
-            ptx::umma_commit(&aempty[sa]);
+              ptx::umma_ss<PAIR>(d_tmem, a_skip0 + a_stage + 2 * k, b_skip + e * kBStage16 + 2 * k, idesc, first | k);
+            ptx::umma_commit_to<PAIR>(&aempty[sa]);
           }
           __syncwarp();
           first = 1;
@@ -285,8 +308,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const uint64_t b_desc = b_main0 + b_stage;
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k)
-                  ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, first | kti | k);
-                ptx::umma_commit(&bempty[sb]);
+                  ptx::umma_ss<PAIR>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, first | kti | k);
+                ptx::umma_commit_to<PAIR>(&bempty[sb]);
               }
               __syncwarp();
               b_stage += kBStage16;
@@ -299,7 +322,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             first = 1;
             a_row += kRow16;
           }
-          if (leader) ptx::umma_commit(&aempty[sa]);
+          if (leader) ptx::umma_commit_to<PAIR>(&aempty[sa]);
           __syncwarp();
           a_stage += Cfg::kABytes >> 4;
           if (++sa == Cfg::kAStages) {
@@ -314,9 +337,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           ptx::tc_fence_after();
           if (leader) {
             for (int k = 0; k < p.kc2 / 16; ++k)
-              ptx::umma_bf16_ss(d_tmem, a_skip0 + a_stage + 2 * k, b_skip0 + b_stage + 2 * k, idesc, first | k);
-            ptx::umma_commit(&bempty[sb]);
-            ptx::umma_commit(&aempty[sa]);
+              ptx::umma_ss<PAIR>(d_tmem, a_skip0 + a_stage + 2 * k, b_skip0 + b_stage + 2 * k, idesc, first | k);
+            ptx::umma_commit_to<PAIR>(&bempty[sb]);
+            ptx::umma_commit_to<PAIR>(&aempty[sa]);
           }
           __syncwarp();
           first = 1;
@@ -334,7 +357,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
       }
-      if (leader) ptx::umma_commit(&tfull[acc]);
+      if (leader) ptx::umma_commit_to<PAIR>(&tfull[acc]);
       __syncwarp();
     }
   } else {
@@ -348,9 +371,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int ro = p.pool ? ((r >> 3) * 4 + (fl >> 1)) : r;
     const bool writer = !p.pool || (fl & 1) == 0;
     const uint32_t o_row = static_cast<uint32_t>(ro) * 128u;
+    const uint32_t tempty0 = PAIR ? ptx::mapa(ptx::smem_u32(tempty), 0) : ptx::smem_u32(tempty);
     uint32_t tl = 0, chunk_no = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
-      int m = tile;
+    for (int u = unit0; u < num_units; u += unit_step, ++tl) {
+      int m = PAIR ? 2 * u + rank : u;
       const int f0 = (m % p.tilesF) * kTileF;
       m /= p.tilesF;
       const int t0 = (m % p.tilesT) * kTileT;
@@ -367,7 +391,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (c == BN / 64 - 1) {                    // accumulator fully read: hand it back to the MMA warp
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+          if (lane == 0) {
+            if constexpr (PAIR) ptx::mbar_arrive_remote_relaxed(tempty0 + 8 * acc);     // the leader's barrier
+            else ptx::mbar_arrive(&tempty[acc]);
+          }
         }
         const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 64 + half * 32);
         uint32_t pk[16];
@@ -412,9 +439,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync_all();             // the leader's MMAs also wrote the peer's tensor memory
   if (warp == 2) {
     __syncwarp();
-    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -427,11 +456,30 @@ static int launch_conv_halo(const CUtensorMap& a0, const CUtensorMap& a1, const 
     AMT_CUDA(cudaFuncSetAttribute(conv_halo_kernel<KC, BN, KF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   ConvHaloParams q = p;
-  q.resident = (p.cblks * KF * 3 + p.cblks2 <= Cfg::kBStages) ? 1 : 0;
-  conv_halo_kernel<KC, BN, KF><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, o, q);
-  AMT_CHECK_LAUNCH();
+  q.resident = (!Cfg::kPair && p.cblks * KF * 3 + p.cblks2 <= Cfg::kBStages) ? 1 : 0;
+  if constexpr (Cfg::kPair) {
+    const int units = (p.num_tiles + 1) / 2;
+    const int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AMT_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<KC, BN, KF>, a0, a1, b0, b1, o, q));
+    count_launch();
+  } else {
+    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    conv_halo_kernel<KC, BN, KF><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, o, q);
+    AMT_CHECK_LAUNCH();
+  }
   return 0;
 }
 
@@ -478,9 +526,10 @@ int run_conv_halo(const void* X, int C, const void* X2, int C2, int B, int T, in
   {
     uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)N};
     uint64_t str[1] = {(uint64_t)Ktot * 2};
-    uint32_t box[2] = {(uint32_t)KC, (uint32_t)N};
+    const uint32_t brows = N >= 128 ? N / 2 : N;       // CTA pairs (N >= 128) load half of a weight block each
+    uint32_t box[2] = {(uint32_t)KC, brows};
     AMT_TRY(encode_tmap_bf16(&b0, W, 2, dims, str, box, swizzle_for(KC)));
-    uint32_t box2[2] = {(uint32_t)kc2, (uint32_t)N};
+    uint32_t box2[2] = {(uint32_t)kc2, brows};
     AMT_TRY(encode_tmap_bf16(&b1, W, 2, dims, str, box2, swizzle_for(kc2)));
   }
 
