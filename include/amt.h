@@ -132,6 +132,15 @@ int amt_f1_counts(const float* probs, const float* target, const int32_t* length
                   int n_pitch, int T_stride, const float* thresholds, int n_thr, int64_t* out,
                   amt_stream_t stream);
 
+/* ---- sample-rate conversion -------------------------- */
+/* Polyphase FIR resampling y = decimate_down(filter_h(zero_stuff_up(x))), zero phase (output 0 is
+ * aligned with input 0), i.e. scipy.signal.resample_poly(x, up, down, window=taps) without its gain /
+ * trimming conventions -- the caller passes taps already scaled by `up`.  Stands in for the
+ * soxr resampling inside librosa.load(path, sr=16000) at reference main.py:76.  x [n_in] f32,
+ * y [n_out] f32 with n_out <= ceil(n_in * up / down), taps [n_taps] f32 (odd count), all device. */
+int amt_resample_poly_f32(const float* x, int64_t n_in, float* y, int64_t n_out, const float* taps,
+                          int n_taps, int up, int down, amt_stream_t stream);
+
 /* ---- building blocks exported for tests and profiling ------------------- */
 /* C[M][ldc] (+bias, optional ReLU) = A[M][K] (bf16, row-major) * W[N][K]^T (bf16).
  * tcgen05/TMA kernel; K % 64 == 0, N % 64 == 0.  out_f32 selects f32 or bf16 output. */

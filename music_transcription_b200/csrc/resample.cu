@@ -1,0 +1,71 @@
+// Polyphase FIR sample-rate conversion on the GPU (the step right before
+// the hot path -- librosa.load(path, sr=16000) at reference main.py:76 resamples every recording to
+// 16 kHz before it is split into 30-s chunks, main.py:82-97).
+//
+//   y[n] = sum_k h[k] * x_up[n*down - k + centre],   x_up = x zero-stuffed by `up`
+// evaluated in polyphase form: only every up-th tap meets a non-zero sample, so output n reads the
+// taps of phase (n*down + centre) % up against ~len(h)/up consecutive input samples.  HBM-bound
+// (one read of x, one write of y): a CTA produces a tile of outputs from an input segment staged in
+// shared memory with coalesced loads; taps are read through the read-only cache.  The taps are an
+// argument, so the host chooses the filter (the Python side uses scipy-compatible Kaiser-windowed sinc).
+#include "common.cuh"
+
+namespace amt {
+
+constexpr int kRsTile = 1024;        // outputs per CTA
+constexpr int kRsThreads = 256;
+
+__global__ void __launch_bounds__(kRsThreads)
+resample_poly_kernel(const float* __restrict__ x, long long n_in, float* __restrict__ y, long long n_out,
+                     const float* __restrict__ h, int n_taps, int up, int down, int centre, int seg_len) {
+  extern __shared__ float s_x[];
+  const long long o0 = static_cast<long long>(blockIdx.x) * kRsTile;
+  const long long o1 = min(o0 + kRsTile, n_out);
+  const int taps_per_phase = (n_taps + up - 1) / up;
+  // input index of the newest sample output n needs: floor((n*down + centre) / up); it reaches back
+  // taps_per_phase - 1 samples
+  const long long hi = ((o1 - 1) * down + centre) / up;
+  const long long lo = (o0 * down + centre) / up - (taps_per_phase - 1);
+  const int seg = static_cast<int>(hi - lo + 1);            // <= seg_len
+  for (int i = threadIdx.x; i < seg; i += kRsThreads) {
+    const long long g = lo + i;
+    s_x[i] = (g >= 0 && g < n_in) ? __ldg(x + g) : 0.0f;
+  }
+  __syncthreads();
+  for (long long n = o0 + threadIdx.x; n < o1; n += kRsThreads) {
+    const long long pos = n * down + centre;
+    const int phase = static_cast<int>(pos % up);
+    const int newest = static_cast<int>(pos / up - lo);
+    float acc = 0.0f;
+    int k = phase;
+    for (int j = 0; k < n_taps; ++j, k += up) acc = fmaf(__ldg(h + k), s_x[newest - j], acc);
+    y[n] = acc;
+  }
+  (void)seg_len;
+}
+
+}  // namespace amt
+
+extern "C" int amt_resample_poly_f32(const float* x, int64_t n_in, float* y, int64_t n_out, const float* taps,
+                                     int n_taps, int up, int down, amt_stream_t stream_) {
+  using namespace amt;
+  AMT_REQUIRE(x && y && taps, "resample: NULL argument");
+  AMT_REQUIRE(n_in > 0 && n_out > 0 && up >= 1 && down >= 1 && n_taps >= 1 && (n_taps & 1), "resample: bad sizes (odd tap count)");
+  AMT_TRY(ensure_device());
+  const int centre = (n_taps - 1) / 2;                       // zero-phase: output 0 is aligned with input 0
+  const int taps_per_phase = (n_taps + up - 1) / up;
+  const long long span = (static_cast<long long>(kRsTile - 1) * down + up - 1) / up + taps_per_phase + 2;
+  AMT_REQUIRE(span * 4 <= 200 * 1024, "resample: ratio %d/%d with %d taps needs too large an input tile", up, down, n_taps);
+  const size_t smem = static_cast<size_t>(span) * 4;
+  static size_t attr = 0;
+  if (smem > attr && smem > 48 * 1024) {
+    AMT_CUDA(cudaFuncSetAttribute(resample_poly_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const long long grid = (n_out + kRsTile - 1) / kRsTile;
+  AMT_REQUIRE(grid < (1ll << 31), "resample: output too long");
+  resample_poly_kernel<<<static_cast<unsigned>(grid), kRsThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
+      x, n_in, y, n_out, taps, n_taps, up, down, centre, static_cast<int>(span));
+  AMT_CHECK_LAUNCH();
+  return 0;
+}
