@@ -80,6 +80,16 @@ def polyphase_taps(up: int, down: int) -> np.ndarray:
     return h / h.sum() * up
 
 
+_TAPS_CACHE = {}
+
+
+def _device_taps(up: int, down: int, device) -> torch.Tensor:
+    key = (up, down, str(device))
+    if key not in _TAPS_CACHE:
+        _TAPS_CACHE[key] = torch.from_numpy(polyphase_taps(up, down).astype(np.float32)).to(device)
+    return _TAPS_CACHE[key]
+
+
 def resample(y, orig_sr: int, target_sr: int, device="cuda") -> torch.Tensor:
     """1-D float32 signal at orig_sr -> CUDA float32 tensor at target_sr (ceil(n * target / orig) samples)."""
     y = torch.as_tensor(y, dtype=torch.float32).to(device).contiguous()
@@ -91,7 +101,7 @@ def resample(y, orig_sr: int, target_sr: int, device="cuda") -> torch.Tensor:
     g = math.gcd(int(orig_sr), int(target_sr))
     up, down = int(target_sr) // g, int(orig_sr) // g
     n_out = -(-y.numel() * up // down)
-    taps = torch.from_numpy(polyphase_taps(up, down).astype(np.float32)).to(y.device)
+    taps = _device_taps(up, down, y.device)
     out = torch.empty(n_out, dtype=torch.float32, device=y.device)
     with torch.cuda.device(y.device):
         _lib.check(_lib.lib().amt_resample_poly_f32(_lib.ptr(y), y.numel(), _lib.ptr(out), n_out, _lib.ptr(taps),

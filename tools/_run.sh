@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_audio.py -q -m gpu --timeout 120 2>&1 | tail -12
-timeout 900 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -3
+ncu --set full --clock-control none -k regex:resample -c 2 -f -o gpurun_out/prof_resample python tools/bench_stages.py --iters 4 > gpurun_out/ncu_rs.log 2>&1; tail -2 gpurun_out/ncu_rs.log
