@@ -228,3 +228,93 @@ def transcribe_chunks(model, wav: torch.Tensor, threshold: float = THRESHOLD, sr
                                                _lib.stream_ptr(wav.device)))
     notes = extract_notes(probs, threshold=threshold)
     return notes, (probs if return_probs else None)
+
+
+class StreamingTranscriber:
+    """Host buffers in, host piano-rolls + note lists out, batch after batch, with the copies of batch i+1
+    (pinned host audio -> device) and of batch i-1 (rolls and notes -> pinned host) overlapped with the compute
+    of batch i: three CUDA streams, two buffer slots.  This is the end-to-end form of main.py:258-275 for a
+    long recording -- every batch still pays its H2D and D2H, they just no longer sit on the critical path.
+
+        st = StreamingTranscriber(model, chunks_per_batch=64)
+        for roll, notes in st.run(pinned_batches):      # roll: pinned (C, 88, T) float {0,1}; notes: (n, 3) int32
+            ...
+    ``notes`` are grouped per batch (frame indices relative to the batch); ``sharding.stitch_notes`` merges
+    batches / ranks exactly like grouping the concatenated roll."""
+
+    class _Slot:
+        pass
+
+    def __init__(self, model, chunks_per_batch: int, n_samples: int = int(CHUNK_LENGTH * SR), threshold: float = THRESHOLD,
+                 sr=SR, n_mels=N_MELS, hop_length=HOP_LENGTH):
+        self.model, self.C, self.thr = model, chunks_per_batch, float(threshold)
+        dev = torch.device(model.device)
+        _lib.require_cuda(torch.empty(0, device=dev), "StreamingTranscriber device")
+        self.dev = dev
+        self.fe = Frontend.get(sr, n_mels, hop_length, dev)
+        self.T = self.fe.num_frames(n_samples)
+        C, T = chunks_per_batch, self.T
+        cap = 88 * ((C * T + 1) // 2)
+        self.copy_in, self.copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.slots = []
+        for _ in range(2):
+            s = StreamingTranscriber._Slot()
+            s.wav = torch.empty(C, n_samples, device=dev)
+            s.probs = torch.empty(C, 88, T, device=dev)
+            s.roll = torch.empty(C, 88, T, device=dev)
+            s.notes = torch.empty(cap, 3, dtype=torch.int32, device=dev)
+            s.counts = torch.zeros(89, dtype=torch.int32, device=dev)
+            s.host_roll = torch.empty(C, 88, T, dtype=torch.float32).pin_memory()
+            s.host_counts = torch.zeros(89, dtype=torch.int32).pin_memory()
+            s.host_notes = torch.empty(cap, 3, dtype=torch.int32).pin_memory()
+            s.h2d_done, s.compute_done, s.counts_done, s.d2h_done = (torch.cuda.Event() for _ in range(4))
+            s.n = C
+            self.slots.append(s)
+        self.h2d_bytes = C * n_samples * 4
+        self.roll_bytes = C * 88 * T * 4 + 89 * 4
+
+    def _launch(self, i: int, host_wav: torch.Tensor) -> None:
+        s = self.slots[i & 1]
+        compute = torch.cuda.current_stream(self.dev)
+        n = host_wav.shape[0]
+        s.n = n
+        with torch.cuda.stream(self.copy_in):
+            self.copy_in.wait_event(s.compute_done)             # the compute that last read this slot's audio is done
+            s.wav[:n].copy_(host_wav, non_blocking=True)
+            s.h2d_done.record(self.copy_in)
+        compute.wait_event(s.h2d_done)
+        compute.wait_event(s.d2h_done)                          # this slot's previous results have left the device
+        mel = self.fe.logmel(s.wav[:n])
+        logits = self.model(mel)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), self.thr, _lib.ptr(s.probs),
+                                                        _lib.ptr(s.roll), _lib.stream_ptr(self.dev)))
+        extract_notes_async(s.probs[:n], self.thr, s.notes, s.counts)
+        s.compute_done.record(compute)
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(s.compute_done)
+            s.host_roll[:n].copy_(s.roll[:n], non_blocking=True)
+            s.host_counts.copy_(s.counts, non_blocking=True)
+            s.counts_done.record(self.copy_out)
+
+    def _finish(self, i: int):
+        s = self.slots[i & 1]
+        s.counts_done.synchronize()                             # host waits; the GPU is already on the next batch
+        total = int(s.host_counts[88])
+        if total > s.notes.shape[0]:
+            raise _lib.AmtError(f"StreamingTranscriber: {total} notes exceed the buffer")
+        with torch.cuda.stream(self.copy_out):
+            s.host_notes[:total].copy_(s.notes[:total], non_blocking=True)
+            s.d2h_done.record(self.copy_out)
+        s.d2h_done.synchronize()
+        return s.host_roll[:s.n], s.host_notes[:total].numpy()
+
+    def run(self, host_batches):
+        """host_batches: iterable of pinned float32 (c <= chunks_per_batch, n_samples) tensors."""
+        i = -1
+        for i, hb in enumerate(host_batches):
+            self._launch(i, hb)
+            if i > 0:
+                yield self._finish(i - 1)
+        if i >= 0:
+            yield self._finish(i)

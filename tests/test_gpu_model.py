@@ -209,3 +209,20 @@ def test_two_hour_recording_240_chunks_batch_invariance_and_notes():
     solo = m(fe.logmel(wav[100:101]))
     batch = m(fe.logmel(wav[96:112]))
     assert torch.equal(solo[0], batch[4])
+
+
+def test_streaming_transcriber_equals_batch_by_batch_path():
+    """Overlapped H2D / compute / D2H (3 streams, 2 slots) must return exactly what the plain per-batch path does,
+    including a short last batch and slot reuse (5 batches over 2 slots)."""
+    sd = synth.synth_state_dict("cnn_rnn", 320, 128, 1, seed=5, gain=2.0)
+    m = TranscriptionModel("cnn_rnn", n_mels=320, hidden_size=128, num_layers=1, device=DEV)
+    m.load_state_dict(sd)
+    base = synth.cheap_wave_batch(8, 480000, seed=11)
+    batches = [(base[:4] * (1.0 - 0.1 * k)).contiguous().pin_memory() for k in range(4)] + [base[4:6].contiguous().pin_memory()]
+    st = pipeline.StreamingTranscriber(m, 4, 480000, 0.5)
+    got = [(r.clone(), n.copy()) for r, n in st.run(batches)]
+    assert len(got) == 5
+    for hb, (roll, notes) in zip(batches, got):
+        want_notes, probs = pipeline.transcribe_chunks(m, hb.to(DEV), threshold=0.5, batch=4, return_probs=True)
+        assert np.array_equal(notes, want_notes)
+        assert torch.equal(roll, (probs > 0.5).float().cpu())
