@@ -146,13 +146,18 @@ int amt_resample_poly_f32(const float* x, int64_t n_in, float* y, int64_t n_out,
  * tcgen05/TMA kernel; K % 64 == 0, N % 64 == 0.  out_f32 selects f32 or bf16 output. */
 int amt_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int M, int N, int K,
                   int ldc, int relu, int out_f32, amt_stream_t stream);
-/* Implicit-GEMM convolution over activations X [B][T][F][Cin] bf16 (Cin % 64 == 0):
- * Y[B][T][F or F/2][Cout] = act(conv_{kf x kt}(X) (+ 1x1 conv of X2) + bias), optional
- * 2:1 max-pool over F.  W [Cout][kf*kt*Cin (+Cin2)] bf16 with K index (tap, cin). */
+/* Halo-tile implicit-GEMM convolution (reference models/cnn_rnn_model.py:35-38, :83-99, :196-201 with
+ * BatchNorm folded) over activations X [B][T][F][Cin] bf16 (Cin = 32 or a multiple of 64):
+ * Y[B][T][F or F/2][Cout] = act(conv_{kf x kt}(X) (+ 1x1 conv of X2 [B][T][F][Cin2]) + bias), optional
+ * 2:1 max-pool over F.  W [Cout][kf*kt*Cin (+Cin2)] bf16 with K index (kf, kt, cin).
+ * Built filters: 3x3 and 7x3 (kf x kt); Cout in {64, 128, 256}; Cin2 in {0, 32, 64k} and <= the
+ * main channel block. */
 int amt_conv_bf16(const void* X, const void* X2, const void* W, const float* bias, void* Y, int B, int T,
                   int F, int Cin, int Cin2, int Cout, int kf, int kt, int relu, int pool,
                   amt_stream_t stream);
-/* Bidirectional-LSTM recurrence over precomputed input projections; see DESIGN.md. */
+/* LSTM recurrence (nn.LSTM eval forward, gate order i,f,g,o; reference models/cnn_rnn_model.py:45-52,
+ * :212-228) over precomputed input projections gx = x W_ih^T + b_ih + b_hh, for n_seq independent
+ * sequences (directions / stacked LSTMs) at once; see DESIGN.md section 4. */
 typedef struct amt_lstm_seq {
   const void* whh;      /* bf16 [4H][H], rows in slice order */
   const float* gx;      /* f32 [B*T][ld_gx], this sequence's first column */
@@ -166,7 +171,8 @@ size_t amt_lstm_scratch_bytes(const amt_lstm_seq* seqs, int n_seq, int B);
 int amt_lstm_recurrence(const amt_lstm_seq* seqs_host, int n_seq, int B, int T, void* scratch,
                         size_t scratch_bytes, amt_stream_t stream);
 /* Clamped softmax attention (reference models/cnn_rnn_model.py:118-139, middle part):
- * qkv bf16 [B*T][3*D] (q|k|v, each [heads][hd]) -> out bf16 [B*T][D]. */
+ * qkv bf16 [B*T][3*D] (q|k|v, each [heads][hd]) -> out bf16 [B*T][D].  head_dim 64/128/192 run the
+ * tcgen05 kernel, 48/96/144 the mma.sync one. */
 int amt_attention_bf16(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip,
                        amt_stream_t stream);
 

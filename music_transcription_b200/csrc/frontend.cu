@@ -71,7 +71,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples, int T, FrontendDev fe,
               float* __restrict__ out, float* __restrict__ chunk_max, int vec_ok) {
   extern __shared__ __align__(16) uint8_t smem_fe[];
