@@ -50,7 +50,7 @@ struct ConvHaloParams {
 
 template <int KC, int BN>
 struct ConvHaloCfg {
-  static constexpr bool kPair = BN >= 128;                             // CTA pairs (cta_group::2)
+  static constexpr bool kPair = true;                                  // CTA pairs (cta_group::2)
   static constexpr int kRowBytes = KC * 2;
   static constexpr int kABytes = kHaloF * kHaloT * kRowBytes;          // 36 KB (KC 64) / 18 KB (KC 32)
   static constexpr int kBRows = kPair ? BN / 2 : BN;                   // weight rows this CTA loads per block
@@ -457,7 +457,7 @@ static int launch_conv_halo(const CUtensorMap& a0, const CUtensorMap& a1, const 
     attr_set = true;
   }
   ConvHaloParams q = p;
-  q.resident = (!Cfg::kPair && p.cblks * KF * 3 + p.cblks2 <= Cfg::kBStages) ? 1 : 0;
+  q.resident = (p.cblks * KF * 3 + p.cblks2 <= Cfg::kBStages) ? 1 : 0;
   if constexpr (Cfg::kPair) {
     const int units = (p.num_tiles + 1) / 2;
     const int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
@@ -526,7 +526,7 @@ int run_conv_halo(const void* X, int C, const void* X2, int C2, int B, int T, in
   {
     uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)N};
     uint64_t str[1] = {(uint64_t)Ktot * 2};
-    const uint32_t brows = N >= 128 ? N / 2 : N;       // CTA pairs (N >= 128) load half of a weight block each
+    const uint32_t brows = N / 2;                      // each CTA of a pair loads half of a weight block
     uint32_t box[2] = {(uint32_t)KC, brows};
     AMT_TRY(encode_tmap_bf16(&b0, W, 2, dims, str, box, swizzle_for(KC)));
     uint32_t box2[2] = {(uint32_t)kc2, brows};
