@@ -111,6 +111,20 @@ def test_conv_implicit_gemm_matches_conv2d(B, T, Fq, Ci, Co, kf, kt, pool, skip)
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
+def test_conv_rejects_unsupported_shapes():
+    x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(64, 9 * 64, dtype=torch.bfloat16, device=DEV)
+    b = torch.zeros(64, device=DEV)
+    y = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device=DEV)
+    L = _lib.lib()
+    for bad in (dict(Cin=48), dict(Cout=96), dict(kf=5), dict(kt=1), dict(Cin=32, Cin2=64)):
+        a = dict(Cin=64, Cin2=0, Cout=64, kf=3, kt=3)
+        a.update(bad)
+        with pytest.raises(ValueError):
+            _lib.check(L.amt_conv_bf16(_lib.ptr(x), _lib.ptr(x) if a["Cin2"] else 0, _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), 1, 8, 8,
+                                       a["Cin"], a["Cin2"], a["Cout"], a["kf"], a["kt"], 1, 0, _stream()))
+
+
 # ----------------------------------------------------------------------------- LSTM recurrence
 def _lstm_ref(gx, whh, reverse):
     """gx [B,T,4H] (gate order i,f,g,o, natural), whh [4H,H] bf16; h fed back in bf16 like the kernel."""
