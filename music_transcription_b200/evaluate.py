@@ -79,6 +79,36 @@ def probabilities(model, dataloader, device) -> tuple:
     return P, Y, np.asarray(lens, dtype=np.int32)
 
 
+@torch.no_grad()
+def probabilities_bucketed(model, dataset, device, max_batch: int = 64) -> tuple:
+    """``probabilities`` for an indexable dataset of (mel (1,n_mels,T), roll (88,T)) items, batched by exact
+    length (cached.bucketed_batches): same (probs, rolls, lengths), in dataset order, as the one-at-a-time
+    loop -- equal-length batches are bitwise batch-invariant -- with up to ``max_batch`` chunks per forward."""
+    from . import cached
+    n = len(dataset)
+    per = [None] * n
+    L = _lib.lib()
+    for idx, mel, roll in cached.bucketed_batches(dataset, max_batch):
+        mel = mel.to(device)
+        logits = model(mel)
+        p = torch.empty_like(logits)
+        with torch.cuda.device(logits.device):
+            _lib.check(L.amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), 0.0, _lib.ptr(p), 0,
+                                               _lib.stream_ptr(logits.device)))
+        roll = roll.to(device).float()
+        for k, i in enumerate(idx):
+            per[i] = (p[k], roll[k])
+    Tmax = max(p.shape[-1] for p, _ in per) if n else 1
+    P = torch.zeros(n, 88, Tmax, device=device)
+    Y = torch.zeros(n, 88, Tmax, device=device)
+    lens = np.zeros(n, dtype=np.int32)
+    for i, (p, y) in enumerate(per):
+        P[i, :, :p.shape[-1]] = p
+        Y[i, :, :y.shape[-1]] = y
+        lens[i] = p.shape[-1]
+    return P, Y, lens
+
+
 def evaluate_at_threshold(model, dataloader, dataset_info, threshold, _cache=None) -> float:
     """Mean framewise F1 over the loader at one threshold (reference signature)."""
     device = dataset_info["device"]

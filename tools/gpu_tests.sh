@@ -18,4 +18,5 @@ run ints "notes or f1 or sigmoid" tests/test_gpu_kernels.py
 run frontend "frontend or logmel" tests/test_gpu_model.py
 run model "model or transcribe" tests/test_gpu_model.py
 run audio "resampler or transcribe_audio" tests/test_audio.py
+run cached "bucketed" tests/test_cached.py
 cat gpurun_out/summary.txt
