@@ -323,7 +323,13 @@ int run_gemm(const void* A, const void* W, const float* bias, void* C, int M, in
   p.kblocks = K / 64;
   p.n_tiles = N / BN;
   p.m_tiles = ceil_div(M, 2 * kBlockM);
-  p.group_n = p.n_tiles > 8 ? 8 : p.n_tiles;
+  // n-tiles per rasterisation group: as many as keep the group's weight slab (group_n x BN x K bf16) around
+  // 40 MB, i.e. L2-resident next to the streaming activations -- 8 tiles for K = 10240 (measured best),
+  // every tile for the K <= 1536 projections, whose activations are then read from DRAM once.
+  const long long tile_bytes = static_cast<long long>(BN) * K * 2;
+  long long g = (40ll << 20) / tile_bytes;
+  g = g < 1 ? 1 : g;
+  p.group_n = p.n_tiles > g ? static_cast<int>(g) : p.n_tiles;
   const long long nt = static_cast<long long>(p.m_tiles) * p.n_tiles;
   AMT_REQUIRE(nt < (1ll << 31), "gemm: too many tiles");
   p.num_tiles = static_cast<int>(nt);
