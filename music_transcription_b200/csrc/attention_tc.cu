@@ -242,15 +242,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (lane == 0) ptx::mbar_arrive(&s_empty[s]);
         const int key0 = j * kAttK + half * 32;
         uint32_t pk[16];
+        float ls0 = 0.0f, ls1 = 0.0f;                // two independent sum chains
+        if (key0 + 32 <= p.T) {                      // every key of this warp's slice is real: no mask
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float x0 = fminf(fmaxf(__uint_as_float(v[2 * i]) * sl2, -cl2), cl2);
-          const float x1 = fminf(fmaxf(__uint_as_float(v[2 * i + 1]) * sl2, -cl2), cl2);
-          const float p0 = key0 + 2 * i < p.T ? ptx::ex2_approx(x0) : 0.0f;
-          const float p1 = key0 + 2 * i + 1 < p.T ? ptx::ex2_approx(x1) : 0.0f;
-          lsum += p0 + p1;
-          pk[i] = ptx::pack_bf16(p0, p1);
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ptx::ex2_approx(fminf(fmaxf(__uint_as_float(v[2 * i]) * sl2, -cl2), cl2));
+            const float p1 = ptx::ex2_approx(fminf(fmaxf(__uint_as_float(v[2 * i + 1]) * sl2, -cl2), cl2));
+            ls0 += p0;
+            ls1 += p1;
+            pk[i] = ptx::pack_bf16(p0, p1);
+          }
+        } else {                                     // the block that straddles T: keys >= T contribute 0
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x0 = fminf(fmaxf(__uint_as_float(v[2 * i]) * sl2, -cl2), cl2);
+            const float x1 = fminf(fmaxf(__uint_as_float(v[2 * i + 1]) * sl2, -cl2), cl2);
+            const float p0 = key0 + 2 * i < p.T ? ptx::ex2_approx(x0) : 0.0f;
+            const float p1 = key0 + 2 * i + 1 < p.T ? ptx::ex2_approx(x1) : 0.0f;
+            ls0 += p0;
+            ls1 += p1;
+            pk[i] = ptx::pack_bf16(p0, p1);
+          }
         }
+        lsum += ls0 + ls1;
         ptx::mbar_wait(&p_empty[s], ph ^ 1);       // O += P_{g-2} V_{g-2} has consumed this buffer
         uint8_t* pbuf = p_smem + s * Cfg::kPBytes;
 #pragma unroll
