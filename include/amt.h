@@ -76,7 +76,7 @@ enum amt_model_kind { AMT_MODEL_CNN_RNN = 0, AMT_MODEL_CNN_RNN_LARGE = 1 };
 typedef struct amt_model_config {
   int kind;             /* amt_model_kind */
   int n_mels;
-  int hidden;           /* LSTM hidden size (multiple of 128, <= 768) */
+  int hidden;           /* LSTM hidden size: multiple of 128, <= 640 (<= 512 with attention) */
   int layers;           /* layers of the main BiLSTM */
   int heads;            /* attention heads (8 in the reference) */
   int use_attention;    /* large only */

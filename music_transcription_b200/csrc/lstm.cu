@@ -273,7 +273,7 @@ static int lstm_plan(const amt_lstm_seq* seqs, int n_seq, int B, LstmPlan* plan)
   AMT_REQUIRE(B >= 1, "lstm: empty batch");
   int ctas = 0, Hmax = 0;
   for (int i = 0; i < n_seq; ++i) {
-    AMT_REQUIRE(seqs[i].H % 64 == 0 && seqs[i].H >= 64 && seqs[i].H <= 768, "lstm: hidden size %d unsupported (multiple of 64, <= 768)",
+    AMT_REQUIRE(seqs[i].H % 64 == 0 && seqs[i].H >= 64 && seqs[i].H <= 704, "lstm: hidden size %d unsupported (multiple of 64, <= 704: the W_hh slice must fit shared memory)",
                 seqs[i].H);
     ctas += seqs[i].H / 32;
     Hmax = seqs[i].H > Hmax ? seqs[i].H : Hmax;

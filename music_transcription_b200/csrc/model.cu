@@ -300,8 +300,8 @@ int amt_model_create(const amt_model_config* cfg, amt_model** out) {
   using namespace amt;
   AMT_REQUIRE(cfg && out, "model_create: NULL argument");
   AMT_REQUIRE(cfg->kind == AMT_MODEL_CNN_RNN || cfg->kind == AMT_MODEL_CNN_RNN_LARGE, "model_create: unknown kind %d", cfg->kind);
-  AMT_REQUIRE(cfg->hidden % 128 == 0 && cfg->hidden >= 128 && cfg->hidden <= 768,
-              "model_create: hidden_size %d unsupported (multiple of 128 in 128..768)", cfg->hidden);
+  AMT_REQUIRE(cfg->hidden % 128 == 0 && cfg->hidden >= 128 && cfg->hidden <= 640,
+              "model_create: hidden_size %d unsupported (multiple of 128 in 128..640)", cfg->hidden);
   AMT_REQUIRE(cfg->layers >= 1 && cfg->layers <= 8, "model_create: num_layers %d unsupported", cfg->layers);
   const bool large = cfg->kind == AMT_MODEL_CNN_RNN_LARGE;
   AMT_REQUIRE(cfg->n_mels >= (large ? 8 : 4) && cfg->n_mels <= 4096, "model_create: n_mels %d unsupported", cfg->n_mels);

@@ -146,7 +146,8 @@ def _lstm_ref(gx, whh, reverse):
 
 @pytest.mark.parametrize("B,T,Hs", [(3, 12, (128,)), (16, 40, (128, 128, 64, 64)), (20, 25, (256, 256)), (5, 30, (512, 512, 256, 256)),
                                     (40, 30, (512, 512)),                    # two batch groups of 32 chunks
-                                    (100, 20, (512, 512, 256, 256))])        # more chunks than co-resident clusters at 32: BC = 64
+                                    (100, 20, (512, 512, 256, 256)),         # more chunks than co-resident clusters at 32: BC = 64
+                                    (3, 10, (640, 640))])                    # 20 slices > one cluster: cooperative L2 fallback
 def test_lstm_recurrence_matches_stepwise_reference(B, T, Hs):
     g = torch.Generator().manual_seed(B * 100 + T)
     L = _lib.lib()
