@@ -11,6 +11,7 @@
 // dot products.  The complex STFT (7.7 MB/chunk) never exists in HBM.  Results are
 // staged as a [n_mels][8] tile so the (B, n_mels, T) output is written in 32-byte runs.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -29,7 +30,7 @@ struct FrontendDev {
   const int* fb_start;     // [n_mels] first FFT bin of each filter
   const int* fb_off;       // [n_mels+1] CSR offsets into fb_w
   const float* fb_w;       // non-zero weights
-  int n_mels, hop;
+  int n_mels, hop, fb_nnz;
 };
 
 // ---- 32-point in-register FFT (radix-2 DIF, output in bit-reversed order) ----
@@ -79,6 +80,11 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
   float* s_x = reinterpret_cast<float*>(smem_fe);                   // [span]
   float2* s_z = reinterpret_cast<float2*>(s_x + ((span + 3) & ~3));  // [warps][32*33] transpose / spectrum / power
   float* s_out = reinterpret_cast<float*>(s_z + kWarpsPerCta * 32 * 33);   // [n_mels][8]
+  // the banded filterbank (CSR: start bin, offsets, weights) staged in smem: lanes walk different filters, so
+  // reading it from global is a 32-address gather per tap; from shared memory it is a 2-4-way bank conflict
+  int* s_fb_start = reinterpret_cast<int*>(s_out + fe.n_mels * kFramesPerCta);   // [n_mels]
+  int* s_fb_off = s_fb_start + fe.n_mels;                                        // [n_mels + 1]
+  float* s_fb_w = reinterpret_cast<float*>(s_fb_off + fe.n_mels + 1);            // [fb_nnz]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
@@ -97,7 +103,14 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(s_x + i)), "l"(x + (ok ? g : 0)), "r"(sz)
                    : "memory");
     }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // (filterbank tables: L2-resident, loaded while the samples are in flight)
+  for (int i = tid; i < fe.n_mels; i += blockDim.x) s_fb_start[i] = __ldg(fe.fb_start + i);
+  for (int i = tid; i <= fe.n_mels; i += blockDim.x) s_fb_off[i] = __ldg(fe.fb_off + i);
+  for (int i = tid; i < fe.fb_nnz; i += blockDim.x) s_fb_w[i] = __ldg(fe.fb_w + i);
+  if (vec_ok) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
     for (int i0 = tid; i0 < span; i0 += blockDim.x * 8) {
       float v[8];
@@ -131,11 +144,17 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
       }
       fft32(v);                                           // over n1 -> k1 (bit-reversed slots)
       // twiddle W_1024^(n2*k1), then transpose through smem: zw[k1][n2]
+      // (powers of w = W_1024^lane by recurrence, re-seeded from the table every 8 steps: 4 table gathers per
+      //  lane instead of 32 -- a 32-address gather costs the LSU ~32 cycles -- at < 1e-6 relative error)
+      {
+        float2 tw = make_float2(1.0f, 0.0f);
+        const float2 w1 = __ldg(fe.tw1024 + lane);
 #pragma unroll
-      for (int sidx = 0; sidx < 32; ++sidx) {
-        const int k1 = bitrev5(sidx);
-        const float2 w = __ldg(fe.tw1024 + ((lane * k1) & 1023));
-        zw[k1 * 33 + lane] = cmul(v[sidx], w);
+        for (int k1 = 0; k1 < 32; ++k1) {
+          if ((k1 & 7) == 0 && k1 > 0) tw = __ldg(fe.tw1024 + ((lane * k1) & 1023));
+          zw[k1 * 33 + lane] = cmul(v[bitrev5(k1)], tw);
+          tw = cmul(tw, w1);
+        }
       }
       __syncwarp();
 #pragma unroll
@@ -163,12 +182,12 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
       // banded mel projection + dB.  power(j) = j <= 512 ? zw[j].x : zw[1024-j].y
       const float* pf = reinterpret_cast<const float*>(zw);
       for (int m = lane; m < fe.n_mels; m += 32) {
-        const int s = __ldg(fe.fb_start + m), o0 = __ldg(fe.fb_off + m), o1 = __ldg(fe.fb_off + m + 1);
+        const int o0 = s_fb_off[m], o1 = s_fb_off[m + 1];
         float acc = 0.0f;
-        for (int j = o0; j < o1; ++j) {
-          const int bin = s + j - o0;
-          const int idx = bin <= kHalf / 2 ? 2 * bin : 2 * (kHalf - bin) + 1;
-          acc = fmaf(__ldg(fe.fb_w + j), pf[idx], acc);
+        const int st = s_fb_start[m];
+        for (int j = o0; j < o1; ++j) {                    // power(bin) = bin <= 512 ? zw[bin].x : zw[1024-bin].y
+          const int bin = st + j - o0;
+          acc = fmaf(s_fb_w[j], pf[bin <= kHalf / 2 ? 2 * bin : 2 * (kHalf - bin) + 1], acc);
         }
         const float db = 10.0f * log10f(fmaxf(acc, 1e-10f));
         s_out[m * kFramesPerCta + fi] = db;
@@ -317,6 +336,7 @@ int amt_frontend_create(int sr, int n_fft, int hop, int n_mels, double fmin, dou
   fe->dev.fb_off = reinterpret_cast<const int*>(db + o_off);
   fe->dev.fb_w = reinterpret_cast<const float*>(db + o_w);
   fe->dev.n_mels = n_mels;
+  fe->dev.fb_nnz = static_cast<int>(w.size());
   fe->dev.hop = hop;
   *out = fe;
   return 0;
@@ -350,7 +370,8 @@ int amt_logmel_f32(amt_frontend* fe, const float* wav, int B, int n_samples, int
   const int T = 1 + n_samples / fe->hop;
   const int span = (kFramesPerCta - 1) * fe->hop + kNfft;
   const size_t smem = sizeof(float) * ((span + 3) & ~3) + sizeof(float2) * kWarpsPerCta * 32 * 33 +
-                      sizeof(float) * fe->n_mels * kFramesPerCta;
+                      sizeof(float) * fe->n_mels * kFramesPerCta + sizeof(int) * (2 * fe->n_mels + 1) +
+                      sizeof(float) * fe->dev.fb_nnz;
   static size_t attr = 0;
   if (smem > attr) {
     AMT_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
