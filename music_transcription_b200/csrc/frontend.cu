@@ -106,12 +106,15 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   // (filterbank tables: L2-resident, loaded while the samples are in flight)
-  for (int i = tid; i < fe.n_mels; i += blockDim.x) s_fb_start[i] = __ldg(fe.fb_start + i);
-  for (int i = tid; i <= fe.n_mels; i += blockDim.x) s_fb_off[i] = __ldg(fe.fb_off + i);
-  for (int i = tid; i < fe.fb_nnz; i += blockDim.x) s_fb_w[i] = __ldg(fe.fb_w + i);
-  if (vec_ok) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-  } else {
+  auto cp4 = [](void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ptx::smem_u32(dst)), "l"(src) : "memory");
+  };
+  for (int i = tid; i < fe.n_mels; i += blockDim.x) cp4(s_fb_start + i, fe.fb_start + i);
+  for (int i = tid; i <= fe.n_mels; i += blockDim.x) cp4(s_fb_off + i, fe.fb_off + i);
+  for (int i = tid; i < fe.fb_nnz; i += blockDim.x) cp4(s_fb_w + i, fe.fb_w + i);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (!vec_ok) {
     for (int i0 = tid; i0 < span; i0 += blockDim.x * 8) {
       float v[8];
 #pragma unroll
