@@ -26,7 +26,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
-LOGMEL_MAX_DB, LOGMEL_MEAN_DB = 2e-2, 5e-4
+LOGMEL_MAX_DB, LOGMEL_MEAN_DB = 3e-3, 1e-4          # dB, vs the fp64-FFT oracle (measured: <= 1.5e-3 max, <= 2.5e-5 mean)
 LOGIT_MAX, PROB_MAX, PROB_MEAN = 0.2, 4e-2, 4e-3
 
 
