@@ -15,7 +15,8 @@
 //            so no transposed copy of V exists; S_{j+1} is issued before O += P_j V_j so the tensor
 //            pipe works while the softmax warps turn S_j into P_j.
 //   warps 3-10  softmax: tcgen05.ld S (two warps per TMEM lane quarter, 32 keys each), scale, clamp,
-//            exp, mask keys >= T, row sums in fp32, P as bf16 into a swizzled smem A-operand tile;
+//            exp, mask keys >= T, row sums in fp32, P as bf16 pairs back into TENSOR MEMORY (tcgen05.st),
+//            where it is the A operand of the TS-form MMA O += P V;
 //            at the end of the tile O / rowsum -> bf16 -> smem -> TMA store (rows >= T clipped).
 // Persistent over (chunk, head, query tile); every ring is indexed by a global key-block counter.
 #include "kernels.cuh"
@@ -42,6 +43,7 @@ struct AttCfg {
   static constexpr int kPBytes = kAttQ * 128;               // one P block (128 q x 64 keys)
   static constexpr int kSmemBytes = kQBytes + 4 * kKVBytes + 2 * kPBytes + 2 * kAttQ * 4 + 1024 + 256;
   static constexpr int kColO = 128;                         // TMEM: S0 [0,64), S1 [64,128), O [128, 128+HD)
+  static constexpr int kColP = 320;                         //       P0 [320,352), P1 [352,384): bf16 pairs, A operand of O += P V
   static constexpr int kTmemCols = 512;
 };
 
@@ -165,7 +167,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     constexpr uint32_t idesc_o = att_idesc_b_mn(kAttQ, HD);
     const uint64_t q_desc = ptx::umma_desc_sw128(ptx::smem_u32(q_smem));
     const uint64_t k_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(k_smem));
-    const uint64_t p_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(p_smem));
     const uint64_t v_desc0 = att_desc_mn(ptx::smem_u32(v_smem), kAttK * 128);
     const uint32_t o_tmem = tmem_base + Cfg::kColO;
     uint32_t g = 0, tl = 0;
@@ -177,11 +178,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (first_of_tile) ptx::mbar_wait(o_empty, (tl & 1) ^ 1);    // previous tile's O has been read out
       ptx::tc_fence_after();
       if (leader) {
-        const uint64_t pd = p_desc0 + static_cast<uint64_t>((s * Cfg::kPBytes) >> 4);
+        const uint32_t pt = tmem_base + Cfg::kColP + s * (kAttK / 2);
         const uint64_t vd = v_desc0 + static_cast<uint64_t>((s * Cfg::kKVBytes) >> 4);
 #pragma unroll
-        for (int k = 0; k < kAttK / 16; ++k)       // 16 keys per MMA: 32 B along a P row, 2 KB down the V block
-          ptx::umma_bf16_ss(o_tmem, pd + 2 * k, vd + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o,
+        for (int k = 0; k < kAttK / 16; ++k)       // 16 keys per MMA: 8 TMEM columns of P, 2 KB down the V block
+          ptx::umma_bf16_ts(o_tmem, pt + 8 * k, vd + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o,
                             (first_of_tile && k == 0) ? 0u : 1u);
         ptx::umma_commit(&p_empty[s]);
         ptx::umma_commit(&v_empty[s]);
@@ -266,12 +267,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         lsum += ls0 + ls1;
         ptx::mbar_wait(&p_empty[s], ph ^ 1);       // O += P_{g-2} V_{g-2} has consumed this buffer
-        uint8_t* pbuf = p_smem + s * Cfg::kPBytes;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(pbuf + ptx::sw128_offset(row, half * 4 + c)) =
-              make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        ptx::fence_proxy_async_smem();
+        // P stays in TENSOR MEMORY (lane = query row, 32-bit column = two keys): it is the A operand of the
+        // TS-form MMA, so it never crosses shared memory -- with S = Q K^T re-reading the Q tile every block the
+        // kernel was shared-memory-bandwidth bound
+        ptx::tmem_st_32x32b_x16(tmem_base + lane_addr + Cfg::kColP + s * (kAttK / 2) + half * 16, pk);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&p_full[s]);
       }
