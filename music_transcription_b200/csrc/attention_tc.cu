@@ -11,6 +11,8 @@
 //   warp 0   TMA loader: Q once per tile, K and V blocks through two 2-deep rings
 //   warp 1   MMA issuer:  S_j = Q K_j^T        (M 128, N 64,  K = hd)   -> TMEM S[j&1]
 //                         O  += P_j V_j        (M 128, N hd,  K = 64)   -> TMEM O
+//            Both A operands (Q, copied once per tile by the softmax warps, and P) live in tensor memory
+//            (TS-form MMAs): shared memory only feeds K and V.
 //            V is consumed as it lies in memory ([key][hd], hd contiguous) as an MN-major B operand,
 //            so no transposed copy of V exists; S_{j+1} is issued before O += P_j V_j so the tensor
 //            pipe works while the softmax warps turn S_j into P_j.
@@ -44,6 +46,7 @@ struct AttCfg {
   static constexpr int kSmemBytes = kQBytes + 4 * kKVBytes + 2 * kPBytes + 2 * kAttQ * 4 + 1024 + 256;
   static constexpr int kColO = 128;                         // TMEM: S0 [0,64), S1 [64,128), O [128, 128+HD)
   static constexpr int kColP = 320;                         //       P0 [320,352), P1 [352,384): bf16 pairs, A operand of O += P V
+  static constexpr int kColQ = 384;                         //       Q  [384, 384 + HD/2): bf16 pairs, A operand of S = Q K^T
   static constexpr int kTmemCols = 512;
 };
 
@@ -87,7 +90,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_empty = bars + 16;
   uint64_t* o_full = bars + 18;     // [1]
   uint64_t* o_empty = bars + 19;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* qt_full = bars + 20;    // [1] Q tile copied into tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,7 +104,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 1) {
     if (lane == 0) {
       ptx::mbar_init(q_full, 1);
-      ptx::mbar_init(q_empty, 1);
+      ptx::mbar_init(q_empty, 8);
+      ptx::mbar_init(qt_full, 8);
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&k_full[i], 1);
         ptx::mbar_init(&k_empty[i], 1);
@@ -165,7 +170,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const bool leader = ptx::elect_one_sync();
     constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(kAttQ, kAttK);
     constexpr uint32_t idesc_o = att_idesc_b_mn(kAttQ, HD);
-    const uint64_t q_desc = ptx::umma_desc_sw128(ptx::smem_u32(q_smem));
     const uint64_t k_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(k_smem));
     const uint64_t v_desc0 = att_desc_mn(ptx::smem_u32(v_smem), kAttK * 128);
     const uint32_t o_tmem = tmem_base + Cfg::kColO;
@@ -190,7 +194,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
     };
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
-      ptx::mbar_wait(q_full, tl & 1);
+      ptx::mbar_wait(qt_full, tl & 1);
       for (int j = 0; j < p.nb; ++j, ++g) {
         const uint32_t s = g & 1, ph = (g >> 1) & 1;
         ptx::mbar_wait(&k_full[s], ph);
@@ -202,11 +206,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int i = 0; i < NB; ++i)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16_ss(tmem_base + s * kAttK, q_desc + static_cast<uint64_t>(i * ((kAttQ * 128) >> 4) + 2 * k),
+              ptx::umma_bf16_ts(tmem_base + s * kAttK, tmem_base + Cfg::kColQ + i * 32 + k * 8,
                                 kd + static_cast<uint64_t>(i * ((kAttK * 128) >> 4) + 2 * k), idesc_s, (i | k) != 0 ? 1u : 0u);
           ptx::umma_commit(&k_empty[s]);
           ptx::umma_commit(&s_full[s]);
-          if (j == p.nb - 1) ptx::umma_commit(q_empty);
         }
         __syncwarp();
         if (j > 0) issue_pv(g - 1, j == 1);
@@ -231,6 +234,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int head = m % p.heads;
       const int b = m / p.heads;
       float lsum = 0.0f;
+      {
+        // Q tile: shared memory (TMA) -> tensor memory, where it is the A operand of the TS-form S = Q K^T for all key
+        // blocks of the tile (an smem-resident Q would be re-read by every one of the 15 x 12 MMAs).  This warp's
+        // share: row `row`, head-dim elements [half*HD/2, +HD/2) = HD/16 sixteen-byte chunks = HD/4 columns.
+        ptx::mbar_wait(q_full, tl & 1);
+        constexpr int kChunks = HD / 16;
+#pragma unroll
+        for (int c4 = 0; c4 < kChunks; c4 += 4) {
+          uint32_t w[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int gc = half * kChunks + c4 + u;          // 16-byte chunk of the row: block gc/8, chunk gc%8
+            const uint4 x = *reinterpret_cast<const uint4*>(q_smem + (gc >> 3) * (kAttQ * 128) + ptx::sw128_offset(row, gc & 7));
+            w[4 * u] = x.x; w[4 * u + 1] = x.y; w[4 * u + 2] = x.z; w[4 * u + 3] = x.w;
+          }
+          ptx::tmem_st_32x32b_x16(tmem_base + lane_addr + Cfg::kColQ + half * (HD / 4) + c4 * 4, w);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(qt_full);
+          ptx::mbar_arrive(q_empty);                         // the smem tile may be refilled with the next tile's Q
+        }
+      }
       for (int j = 0; j < p.nb; ++j, ++g) {
         const uint32_t s = g & 1, ph = (g >> 1) & 1;
         ptx::mbar_wait(&s_full[s], ph);
