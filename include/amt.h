@@ -104,6 +104,9 @@ int amt_model_forward(amt_model* m, const float* logmel, int B, int T, float* fr
  * and returns the number of stages, filling names (cap x 32 chars), total ms and launch counts. */
 int amt_model_profile_enable(amt_model* m, int enable);
 int amt_model_profile_read(amt_model* m, char* names, float* total_ms, int* launches, int cap);
+/* Without blocking: the first profiled stage (since the last read / forward) whose end event has not completed yet --
+ * its position in launch order, name copied to `name`; -1 when nothing is in flight.  Watchdog / hang diagnosis. */
+int amt_model_profile_in_flight(amt_model* m, char* name, int cap);
 
 /* ---- sigmoid / threshold / notes ---------------------------------------- */
 /* probs = sigmoid(logits); roll = (probs > thr) as float {0,1}

@@ -375,6 +375,22 @@ int amt_model_profile_read(amt_model* m, char* names, float* total_ms, int* laun
   return n;
 }
 
+int amt_model_profile_in_flight(amt_model* m, char* name, int cap) {
+  using namespace amt;
+  AMT_REQUIRE(m && name && cap > 0, "model_profile_in_flight: bad arguments");
+  int idx = 0;
+  for (const Profiler::Pending& p : m->prof.pending) {
+    if (cudaEventQuery(p.b) != cudaSuccess) {
+      cudaGetLastError();
+      snprintf(name, cap, "%s", m->prof.stages[p.stage].name.c_str());
+      return idx;
+    }
+    ++idx;
+  }
+  name[0] = 0;
+  return -1;
+}
+
 size_t amt_model_workspace_bytes(const amt_model* m, int B, int T) {
   if (!m || B <= 0 || T <= 0) return 0;
   amt::Buffers b;
