@@ -108,6 +108,18 @@ int amt_model_profile_read(amt_model* m, char* names, float* total_ms, int* laun
  * its position in launch order, name copied to `name`; -1 when nothing is in flight.  Watchdog / hang diagnosis. */
 int amt_model_profile_in_flight(amt_model* m, char* name, int cap);
 
+/* ---- validation loss value (forward only) --------- */
+/* TranscriptionModel.compute_loss for the CNN-RNN models (reference models/transcription_model.py:110-217):
+ * mean binary cross-entropy with logits of frame [B][P][T_logits] against targets [B][P][T_targets]
+ * (logits linearly interpolated along time like F.interpolate(mode="linear", align_corners=False) when the
+ * lengths differ, :140-142); with lengths[B] != NULL only frames t < lengths[b] count and the sum is divided
+ * by max(valid_frames * P, 1) (:148-163).  With onset and offset logits (both or neither) the result is
+ * 0.5 frame + 0.25 onset + 0.25 offset against onset / offset targets derived from the roll (:165-190).
+ * acc: 4 doubles of device scratch; out: 4 floats on the device = {loss, frame, onset, offset}.  Asynchronous. */
+int amt_bce_loss(const float* frame, const float* onset, const float* offset, const float* targets,
+                 const int32_t* lengths, int B, int P, int T_logits, int T_targets, double* acc, float* out,
+                 amt_stream_t stream);
+
 /* ---- sigmoid / threshold / notes ---------------------------------------- */
 /* probs = sigmoid(logits); roll = (probs > thr) as float {0,1}
  * (reference main.py:153-156, models/transcription_model.py:263-266).

@@ -37,6 +37,8 @@ _SIGS = {
     "amt_device_check": (C.c_int, []),
     "amt_launch_count": (C.c_uint64, []),
     "amt_model_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "amt_bce_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "amt_model_profile_in_flight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "amt_model_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
     "amt_frontend_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_void_p)]),

@@ -223,5 +223,50 @@ class TranscriptionModel(nn.Module):
             _lib.check(n)
         return [(names.raw[32 * i:32 * (i + 1)].split(b"\0")[0].decode(), float(ms[i]), int(launches[i])) for i in range(min(n, cap))]
 
+    def profile_in_flight(self):
+        """Without blocking: (position, stage name) of the first profiled stage that has not finished on the GPU,
+        or None when everything launched since profile(True) / the last forward has completed (watchdogs)."""
+        name = C.create_string_buffer(64)
+        idx = _lib.lib().amt_model_profile_in_flight(self._handle, name, 64)
+        return None if idx < 0 else (int(idx), name.value.decode())
+
+    @torch.no_grad()
     def compute_loss(self, logits, targets, lengths=None):
-        raise NotImplementedError("training losses are outside the B200 inference hot path (SURVEY.md section 8f, rank 4)")
+        """The VALUE of the reference's loss (models/transcription_model.py:110-217) as a 0-dim float32 CUDA tensor:
+        mean BCE-with-logits against the piano roll, masked to ``lengths`` frames per sample when given; for the
+        dict of the three-head Large model 0.5 frame + 0.25 onset + 0.25 offset with onset / offset targets derived
+        from the roll.  Logits whose time axis differs from the targets' are linearly interpolated
+        (align_corners=False).  One CUDA pass, asynchronous; forward only -- there is no autograd graph behind it
+        (training is outside the hot path), so it serves validation loops."""
+        heads = logits if isinstance(logits, dict) else {"frame": logits}
+        frame = heads["frame"]
+        _lib.require_cuda(frame, "compute_loss logits")
+        _lib.require_cuda(targets, "compute_loss targets")
+        if frame.dim() != 3 or targets.dim() != 3 or frame.shape[:2] != targets.shape[:2]:
+            raise ValueError(f"compute_loss: logits {tuple(frame.shape)} vs targets {tuple(targets.shape)}")
+        dev = frame.device
+        tensors = [frame.contiguous().float()]
+        if isinstance(logits, dict):
+            for k in ("onset", "offset"):
+                if heads[k].shape != frame.shape:
+                    raise ValueError("compute_loss: head shapes differ")
+                tensors.append(heads[k].contiguous().float())
+        tgt = targets.to(dev).contiguous().float()
+        B, P, Tl = frame.shape
+        Tt = tgt.shape[-1]
+        if B == 0 or Tl == 0 or Tt == 0:
+            raise ValueError("compute_loss: empty input")
+        len_t = None
+        if lengths is not None:
+            len_t = torch.as_tensor(lengths).to(dev).to(torch.int32).contiguous()
+            if len_t.shape != (B,):
+                raise ValueError(f"compute_loss: lengths must have shape ({B},)")
+        acc = torch.empty(4, dtype=torch.float64, device=dev)
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().amt_bce_loss(_lib.ptr(tensors[0]), _lib.ptr(tensors[1]) if len(tensors) == 3 else 0,
+                                               _lib.ptr(tensors[2]) if len(tensors) == 3 else 0, _lib.ptr(tgt),
+                                               _lib.ptr(len_t) if len_t is not None else 0, B, P, Tl, Tt,
+                                               _lib.ptr(acc), _lib.ptr(out), _lib.stream_ptr(dev)))
+        self.last_loss_parts = out[1:]            # frame / onset / offset means (device tensor, same stream)
+        return out[0]

@@ -14,6 +14,8 @@ What is executed from the reference:
   * scripts/evaluate.py evaluate_at_threshold / run_threshold_tuning with the
     globals the script imports under ``__main__`` injected, and a stub model
     -> pins oracle/f1.py and the sweep schedule.
+  * TranscriptionModel.compute_loss (models/transcription_model.py:110-217) on seeded logits / rolls
+    -> pins oracle/losses.py.
   * torchaudio (independent implementation, not the reference) as a
     cross-check of oracle/frontend.py -- librosa itself cannot be run, so the
     frontend stays "parity unpinned".
@@ -240,10 +242,52 @@ def gen_frontend():
                         fb_rowsum=fe.mel_filterbank().sum(1), fb_nnz=(fe.mel_filterbank() > 0).sum(1))
 
 
+# (name, B, T_logits, T_targets, three heads, lengths or None)
+LOSS_CASES = [
+    ("single", 3, 50, 50, False, None),
+    ("single_masked", 4, 61, 61, False, [61, 17, 0, 40]),
+    ("single_interp", 2, 47, 94, False, [94, 30]),
+    ("single_interp_down", 2, 100, 33, False, None),
+    ("heads", 3, 50, 50, True, None),
+    ("heads_masked", 4, 61, 61, True, [61, 17, 1, 200]),
+    ("heads_interp", 2, 30, 45, True, [45, 11]),
+    ("heads_T1", 2, 1, 1, True, None),
+    ("all_masked", 2, 20, 20, True, [0, 0]),
+]
+
+
+def gen_losses():
+    """TranscriptionModel.compute_loss of the reference itself (models/transcription_model.py:110-217) on seeded
+    logits / rolls -> pins oracle/losses.py and the amt_bce_loss kernel."""
+    TM = _ref_modules()
+    small = TM(model_type="cnn_rnn", n_mels=64, hidden_size=128, num_layers=1, device="cpu")
+    out = {}
+    for i, (name, B, Tl, Tt, heads, lengths) in enumerate(LOSS_CASES):
+        g = torch.Generator().manual_seed(100 + i)
+        logits = {k: torch.randn(B, 88, Tl, generator=g) * 3.0 for k in ("frame", "onset", "offset")}
+        # rolls with runs (notes), so onset / offset targets are non-trivial
+        roll = (torch.rand(B, 88, Tt, generator=g) < 0.3).float()
+        roll[:, :, 1:] = torch.maximum(roll[:, :, 1:], (roll[:, :, :-1] * (torch.rand(B, 88, Tt - 1, generator=g) < 0.6)).float()) if Tt > 1 else roll[:, :, 1:]
+        lt = None if lengths is None else torch.tensor(lengths)
+        with torch.no_grad():
+            val = small.compute_loss(logits if heads else logits["frame"], roll, lt)
+        out[f"{name}.frame"], out[f"{name}.onset"], out[f"{name}.offset"] = (logits[k].numpy() for k in ("frame", "onset", "offset"))
+        out[f"{name}.roll"] = roll.numpy()
+        out[f"{name}.lengths"] = np.array([] if lengths is None else lengths, dtype=np.int64)
+        out[f"{name}.heads"] = np.array(int(heads))
+        out[f"{name}.loss"] = np.array(float(val), dtype=np.float64)
+        print("loss", name, float(val))
+    np.savez_compressed(os.path.join(OUT, "loss_reference.npz"), names=np.array([c[0] for c in LOSS_CASES]), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
+    if len(sys.argv) > 1 and sys.argv[1] == "losses":
+        gen_losses()
+        sys.exit(0)
     gen_models()
+    gen_losses()
     gen_notes()
     gen_f1()
     gen_frontend()

@@ -119,6 +119,51 @@ def test_model_matches_reference_golden(path):
     assert (pred.cpu().numpy() != g["pred"]).mean() < 0.02
 
 
+def test_stage_profile_and_in_flight_query():
+    m = TranscriptionModel(model_type="cnn_rnn", n_mels=64, hidden_size=128, num_layers=1, device=DEV)
+    m.load_state_dict(synth.synth_state_dict("cnn_rnn", 64, 128, 1, seed=3))
+    m.eval()
+    x = torch.randn(2, 1, 64, 50, device=DEV)
+    ref = m(x).clone()
+    m.profile(True)
+    out = m(x)
+    torch.cuda.synchronize()
+    assert m.profile_in_flight() is None                 # everything launched has completed
+    stages = m.profile_read()
+    assert torch.equal(out, ref)
+    names = [s[0] for s in stages]
+    assert "conv1" in names and any(n.endswith(".rec") for n in names)
+    assert all(ms > 0 and n == 1 for _, ms, n in stages)
+    m.profile(False)
+
+
+def test_compute_loss_matches_reference_golden_and_oracle():
+    """amt_bce_loss (one CUDA pass, fp64 accumulation) vs the reference's own compute_loss values
+    (tests/golden/loss_reference.npz) and the oracle restatement: relative 2e-6."""
+    from oracle import losses as olosses
+    from tests.test_oracle import _loss_cases
+    m = TranscriptionModel(model_type="cnn_rnn", n_mels=64, hidden_size=128, num_layers=1, device=DEV)
+    for name, logits, roll, lengths, ref in _loss_cases():
+        dl = {k: v.to(DEV) for k, v in logits.items()} if isinstance(logits, dict) else logits.to(DEV)
+        got = m.compute_loss(dl, roll.to(DEV), None if lengths is None else lengths.to(DEV))
+        assert got.shape == () and got.dtype == torch.float32 and got.is_cuda
+        assert abs(float(got) - ref) <= 2e-6 * max(1.0, abs(ref)), (name, float(got), ref)
+    # canonical size, three heads, ragged lengths: against the oracle
+    g = torch.Generator().manual_seed(5)
+    heads = {k: torch.randn(16, 88, 938, generator=g) * 2 for k in ("frame", "onset", "offset")}
+    roll = (torch.rand(16, 88, 938, generator=g) < 0.05).float()
+    lengths = torch.tensor([938, 937, 469, 1] * 4)
+    ref = float(olosses.compute_loss(heads, roll, lengths))
+    got = float(m.compute_loss({k: v.to(DEV) for k, v in heads.items()}, roll.to(DEV), lengths))
+    assert abs(got - ref) <= 2e-6 * ref
+    parts = m.last_loss_parts.cpu()
+    assert abs(float(0.5 * parts[0] + 0.25 * parts[1] + 0.25 * parts[2]) - got) < 1e-6
+    with pytest.raises(ValueError):
+        m.compute_loss(heads["frame"].to(DEV), roll[:, :40].to(DEV))
+    with pytest.raises(Exception):
+        m.compute_loss(heads["frame"], roll)          # CPU tensors: no fallback
+
+
 def test_model_rejects_bad_inputs():
     with pytest.raises(ValueError):
         TranscriptionModel(model_type="nope", device=DEV)

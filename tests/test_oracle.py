@@ -126,3 +126,24 @@ def test_frontend_filterbank_properties():
     assert db.min() == pytest.approx(db.max() - 80.0, abs=1e-4) or db.min() > db.max() - 80.0
     sil = ofe.logmel(np.zeros(48000, np.float32))
     assert np.allclose(sil, -100.0, atol=1e-4)        # amin floor, max-80 is below it
+
+
+def _loss_cases():
+    g = np.load(os.path.join(GOLDEN, "loss_reference.npz"))
+    for name in g["names"]:
+        name = str(name)
+        heads = bool(g[f"{name}.heads"])
+        logits = {k: torch.from_numpy(g[f"{name}.{k}"]) for k in ("frame", "onset", "offset")}
+        lengths = g[f"{name}.lengths"]
+        yield (name, logits if heads else logits["frame"], torch.from_numpy(g[f"{name}.roll"]),
+               None if lengths.size == 0 else torch.from_numpy(lengths), float(g[f"{name}.loss"]))
+
+
+def test_loss_oracle_matches_reference_compute_loss():
+    from oracle import losses as olosses
+    n = 0
+    for name, logits, roll, lengths, ref in _loss_cases():
+        got = float(olosses.compute_loss(logits, roll, lengths))
+        assert abs(got - ref) <= 1e-6 * max(1.0, abs(ref)), (name, got, ref)
+        n += 1
+    assert n == 9
