@@ -55,7 +55,10 @@ struct ConvHaloCfg {
   static constexpr int kABytes = kHaloF * kHaloT * kRowBytes;          // 36 KB (KC 64) / 18 KB (KC 32)
   static constexpr int kBRows = kPair ? BN / 2 : BN;                   // weight rows this CTA loads per block
   static constexpr int kBBytes = kBRows * kRowBytes;
-  static constexpr int kAStages = 3;
+  // activation tiles in flight: 3 when the layer is tensor-bound (BN >= 128); the 64-output layers are HBM-bound and
+  // 3 x 18 KB per SM (8 MB chip-wide) is less than HBM latency x bandwidth, so they get the smem their small weight
+  // blocks leave free
+  static constexpr int kAStages = BN == 64 ? (KC == 32 ? 6 : 4) : 3;
   static constexpr int kOutBytes = 2 * 128 * 128;                      // two staged [128 rows x 64 ch] output chunks
   static constexpr int kBudget = 225 * 1024 - kAStages * kABytes - kOutBytes - BN * 4 - 1024 - 512;
   static constexpr int kBStagesRaw = kBudget / kBBytes;
