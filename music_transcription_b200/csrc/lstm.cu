@@ -7,19 +7,20 @@
 // for several independent sequences at once (forward / reverse directions, the main
 // and the local LSTM, and groups of BC chunks).
 //
-// Decomposition: one CTA (512 threads) per (batch group, sequence, slice of 32 hidden
-// units).  The CTA keeps its 128 x H slice of W_hh (4 gates x 32 units, bf16) resident in
-// shared memory for all T steps as the K-major swizzled A operand of tcgen05.mma; per
-// step it gathers h_{t-1} (BC x H bf16, published by the sibling slices through L2) as
-// the B operand, one thread issues H/16 MMAs into a 128 x BC fp32 TMEM accumulator, and
-// 16 warps finish the cell update: warp w reads TMEM lane quarter w%4, column group w/4
-// (the 4 gates of a unit sit in 4 adjacent lanes of ONE warp, so the gate exchange is a
-// warp-private smem transpose), each thread then owns BC/16 cells whose fp32 cell state
-// never leaves its registers.  Slices of one sequence synchronise per step through a
-// release/acquire counter in global memory; the launch is cooperative so all CTAs are
-// co-resident.  The step is latency-bound, so everything is arranged to shorten the
-// dependent chain: gx prefetched before the wait, all h loads in flight at once, no
-// per-thread fences, 4 warps per scheduler for the transcendental-heavy epilogue.
+// Two kernels share this decomposition -- one CTA (512 threads) per (batch group of BC chunks, sequence, slice of
+// 32 hidden units), 16 warps finishing the cell update (warp w reads TMEM lane quarter w%4, column group w/4; the
+// 4 gates of a unit sit in 4 adjacent lanes of ONE warp, so the gate exchange is a warp-private smem transpose;
+// every thread owns BC/16 cells whose fp32 cell state never leaves its registers):
+//
+//   lstm_cluster_kernel (the product path, H <= 512): the slices of a sequence form a thread-block cluster of CTA
+//     pairs; W_hh lives in TENSOR MEMORY, h_t travels between the CTAs through distributed shared memory with bulk
+//     copies -- see the comment above that kernel.
+//   lstm_recurrence_kernel (fallback for hidden sizes whose slices do not fit one cluster): W_hh slice resident in
+//     shared memory as the K-major swizzled A operand, h_{t-1} gathered from L2 (published by the sibling slices),
+//     one release/acquire counter per step in global memory, cooperative launch so all CTAs are co-resident.
+//
+// The step is latency-bound, so everything is arranged to shorten the dependent chain: gx prefetched a step ahead,
+// no per-thread fences, 4 warps per scheduler for the transcendental-heavy epilogue, outputs stored a step late.
 #include <cooperative_groups.h>
 
 #include <cstdlib>
@@ -300,11 +301,11 @@ static int lstm_plan(const amt_lstm_seq* seqs, int n_seq, int B, LstmPlan* plan)
 // ============================================================================
 // Cluster variant: the slices of one sequence form (part of) a thread-block cluster and
 // exchange h_t through distributed shared memory instead of L2.  Per step every CTA stages
-// its 32 x BC new h values in its own smem, pushes them with 16-byte st.shared::cluster
-// stores straight into the (double-buffered, swizzled) B-operand tile of every peer, and
-// arrives (release.cluster) on the peer's mbarrier; the consumer waits (acquire.cluster) for
-// n_peers arrivals.  No L2 round trips, no spinning on global memory, no cooperative launch:
-// clusters are co-scheduled by hardware and independent of each other.
+// its 32 x BC new h values (pre-swizzled) in its own smem and 16 warps each push one half of that
+// block with ONE bulk DSMEM copy (cp.async.bulk.shared::cluster) straight into the double-buffered
+// B-operand tile of a peer; the copy completes (complete_tx) on the peer's mbarrier, which the
+// consumer waits on.  No L2 round trips, no membar, no spinning on global memory, no cooperative
+// launch: clusters are co-scheduled by hardware and independent of each other.
 // ============================================================================
 constexpr int kMaxClusterCtas = 64;     // CTAs of one batch group (all its clusters)
 constexpr int kWCol0 = 64;              // TMEM columns [0,64): accumulator D; [64, 64 + H/2): W_hh slice
