@@ -178,6 +178,36 @@ def cpu_reference_chunks_per_sec(n_chunks: int, threads: int, repeat: int = 1):
     return n_chunks / best, best
 
 
+def gpu_eager_chunks_per_sec(wav: torch.Tensor, n_chunks: int, reps: int = 3):
+    """SURVEY.md 8(d) 'GPU baseline beside it': the reference's modules as plain torch fp32 eager on this GPU
+    (oracle port: F.conv2d / nn.LSTM / matmul -> cuDNN and cuBLAS kernels, TF32 off as in the reference), fed the
+    log-mel of our frontend, batched like our step.  A reported baseline; nothing of it is on the product path."""
+    from music_transcription_b200 import pipeline, synth
+    from oracle import model as omodel
+    dev = wav.device
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd = {k: v.to(dev) for k, v in synth.synth_state_dict("cnn_rnn_large", N_MELS, HIDDEN, LAYERS, seed=1, gain=3 ** -0.5).items()}
+        mel = pipeline.Frontend.get(device=dev).logmel(wav[:n_chunks]).clone()
+        best = None
+        for _ in range(reps + 1):                              # first pass = warm-up (cuDNN autotune, allocator)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            logits = omodel.large_forward(sd, mel, HIDDEN, LAYERS)
+            roll = (torch.sigmoid(logits) > 0.5).float()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        del roll
+        return n_chunks / (best / 1e3), best
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -221,6 +251,9 @@ def main():
     ap.add_argument("--ref-chunks", type=int, default=2, help="chunks per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-chunks", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-eager-baseline", type=int, default=0, metavar="CHUNKS",
+                    help="also time the oracle port (plain torch fp32 eager: cuDNN / cuBLAS, TF32 off) on this GPU for a batch "
+                         "of CHUNKS chunks -- SURVEY 8d 'GPU baseline beside it'; adds gpu_eager_baseline to the JSON line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -406,6 +439,11 @@ def main():
             line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_baseline_chunks} chunks, B=1 loop as main.py:258-266 ({secs:.1f} s), oracle port, "
                                               f"torch {torch.get_num_threads()} threads"}
+        if world == 1 and args.gpu_eager_baseline > 0:
+            n = min(args.gpu_eager_baseline, C)
+            v, ms_eager = gpu_eager_chunks_per_sec(wav, n)
+            line["gpu_eager_baseline"] = {"value": round(v, 2), "unit": UNIT, "batch_chunks": n, "ms_per_batch": round(ms_eager, 2),
+                                          "kind": "oracle port, torch fp32 eager (cuDNN/cuBLAS, TF32 off), forward + sigmoid + threshold only"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

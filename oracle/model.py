@@ -34,7 +34,7 @@ def _bilstm(x, sd, prefix, hidden, layers):
     """nn.LSTM(batch_first=True, bidirectional=True) in eval mode, fp32
     (reference cnn_rnn_model.py:45-52,212-228; inter-layer dropout is off)."""
     inp = x.shape[-1]
-    rnn = torch.nn.LSTM(inp, hidden, num_layers=layers, batch_first=True, bidirectional=True)
+    rnn = torch.nn.LSTM(inp, hidden, num_layers=layers, batch_first=True, bidirectional=True).to(x.device)
     own = rnn.state_dict()
     rnn.load_state_dict({k: sd[prefix + "." + k] for k in own})
     rnn.eval()
