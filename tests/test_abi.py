@@ -75,3 +75,22 @@ def test_drop_in_state_dict_keys_match_reference_spec():
         assert m.model_type == mt and m.device == "cpu" and m.use_onset_offset_heads == heads
     with pytest.raises(ValueError):
         TranscriptionModel("bogus")
+
+
+def test_product_package_never_touches_the_oracle_or_the_reference_tree():
+    """oracle/ is test infrastructure: nothing under music_transcription_b200/ (Python or CUDA) may import it or
+    read /root/reference; the only other allowed users are bench.py's baseline legs and __graft_entry__.smoke()."""
+    pkg = os.path.join(ROOT, "music_transcription_b200")
+    offenders = []
+    for d, _, files in os.walk(pkg):
+        if "build" in os.path.relpath(d, pkg).split(os.sep):
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            src = open(os.path.join(d, f), errors="replace").read()
+            if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "/root/reference" in src:
+                offenders.append(os.path.relpath(os.path.join(d, f), ROOT))
+    assert offenders == []
+    for f in ("bench.py", "__graft_entry__.py"):          # nothing the GPU box runs may read the reference tree
+        assert "/root/reference" not in open(os.path.join(ROOT, f)).read()
