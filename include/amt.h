@@ -147,6 +147,12 @@ int amt_f1_counts(const float* probs, const float* target, const int32_t* length
                   int n_pitch, int T_stride, const float* thresholds, int n_thr, int64_t* out,
                   amt_stream_t stream);
 
+/* ---- audio decode helper ----------------------------- */
+/* Interleaved 16-bit PCM frames pcm [n_frames][channels] (device) -> mono float32 out [n_frames]: sample / 32768,
+ * channels averaged in float32 -- bit-identical to decoding on the host and taking numpy's float32 mean
+ * (librosa.load(..., mono=True) at reference main.py:76), at half the upload bytes. */
+int amt_pcm16_to_mono_f32(const int16_t* pcm, int64_t n_frames, int channels, float* out, amt_stream_t stream);
+
 /* ---- sample-rate conversion -------------------------- */
 /* Polyphase FIR resampling y = decimate_down(filter_h(zero_stuff_up(x))), zero phase (output 0 is
  * aligned with input 0), i.e. scipy.signal.resample_poly(x, up, down, window=taps) without its gain /

@@ -37,6 +37,7 @@ _SIGS = {
     "amt_device_check": (C.c_int, []),
     "amt_launch_count": (C.c_uint64, []),
     "amt_model_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "amt_pcm16_to_mono_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "amt_bce_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "amt_model_profile_in_flight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

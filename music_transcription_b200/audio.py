@@ -28,8 +28,8 @@ SR = pipeline.SR
 
 
 # ----------------------------------------------------------------------------- decode
-def load_wav(path: str):
-    """RIFF/WAVE -> (float32 array [n_frames, n_channels] in [-1, 1), sample rate)."""
+def _parse_wav(path: str):
+    """RIFF/WAVE container -> (format tag, channels, sample rate, bits per sample, raw data bytes)."""
     data = Path(path).read_bytes()
     if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
         raise ValueError(f"{path}: not a RIFF/WAVE file (other containers need soundfile/audioread, absent here)")
@@ -47,7 +47,23 @@ def load_wav(path: str):
         pos += 8 + size + (size & 1)
     if fmt is None or pcm is None:
         raise ValueError(f"{path}: missing fmt or data chunk")
-    tag, ch, sr, bits = fmt
+    return fmt + (pcm,)
+
+
+def load_wav_pcm16(path: str):
+    """16-bit PCM WAVE -> (int16 array [n_frames, n_channels] exactly as stored, sample rate); None for any other
+    sample format (use load_wav).  The raw samples go to the GPU as they are (``load_audio``)."""
+    tag, ch, sr, bits, pcm = _parse_wav(path)
+    if tag != 1 or bits != 16:
+        return None
+    x = np.frombuffer(pcm[:len(pcm) // 2 * 2], "<i2")
+    n = len(x) // ch
+    return x[:n * ch].reshape(n, ch), int(sr)
+
+
+def load_wav(path: str):
+    """RIFF/WAVE -> (float32 array [n_frames, n_channels] in [-1, 1), sample rate)."""
+    tag, ch, sr, bits, pcm = _parse_wav(path)
     if tag == 1:                                                   # integer PCM
         if bits == 8:
             x = (np.frombuffer(pcm, np.uint8).astype(np.float32) - 128.0) / 128.0
@@ -111,9 +127,20 @@ def resample(y, orig_sr: int, target_sr: int, device="cuda") -> torch.Tensor:
 
 def load_audio(path: str, sr: int = SR, mono: bool = True, device="cuda"):
     """``librosa.load(path, sr=sr, mono=mono)`` for WAVE files -> (CUDA float32 tensor, sr)."""
-    x, file_sr = load_wav(path)
     if not mono:
         raise ValueError("the reference always loads mono (main.py:76)")
+    raw = load_wav_pcm16(path)
+    if raw is not None and raw[0].shape[0] > 0:
+        # the common case: 16-bit PCM goes up as int16 (half the PCIe bytes, no host conversion pass) and becomes
+        # mono float32 on the GPU, bit-identical to the host path below
+        pcm, file_sr = raw
+        dev_pcm = torch.from_numpy(np.ascontiguousarray(pcm)).to(device, non_blocking=True)
+        y = torch.empty(pcm.shape[0], dtype=torch.float32, device=dev_pcm.device)
+        with torch.cuda.device(dev_pcm.device):
+            _lib.check(_lib.lib().amt_pcm16_to_mono_f32(_lib.ptr(dev_pcm), pcm.shape[0], pcm.shape[1], _lib.ptr(y),
+                                                        _lib.stream_ptr(dev_pcm.device)))
+        return resample(y, file_sr, sr, device), sr
+    x, file_sr = load_wav(path)
     y = x.mean(axis=1, dtype=np.float32) if x.shape[1] > 1 else x[:, 0]
     return resample(y, file_sr, sr, device), sr
 
@@ -124,8 +151,7 @@ def transcribe_audio(audio_path, model, output_path=None, threshold=pipeline.THR
     chunks (last one zero padded) -> batched log-mel / forward / sigmoid -> notes grouped on the concatenated
     roll -> Standard MIDI File next to the input (``<stem>_transcription.mid``) unless ``output_path``."""
     y, _ = load_audio(str(audio_path), SR, device=model.device)
-    chunks = pipeline.split_audio_into_chunks(y.cpu().numpy(), pipeline.CHUNK_LENGTH, SR)
-    wav = torch.from_numpy(np.stack(chunks)).to(model.device)
+    wav = pipeline.split_audio_into_chunks(y, pipeline.CHUNK_LENGTH, SR)      # stays on the device: (n_chunks, 480000)
     triples, _ = pipeline.transcribe_chunks(model, wav, threshold=threshold, batch=batch)
     midi = pipeline.NoteList(triples, SR / pipeline.HOP_LENGTH, 21)
     if output_path is None:

@@ -44,6 +44,19 @@ resample_poly_kernel(const float* __restrict__ x, long long n_in, float* __restr
   (void)seg_len;
 }
 
+// 16-bit PCM frames [n_frames][channels] (interleaved, as they lie in a WAVE file) -> mono float32 in [-1, 1):
+// sample / 32768 (exact in fp32), channels averaged as numpy's float32 mean does (exact sum of 16-bit values, one
+// division).  Uploading int16 and converting here moves half the bytes over PCIe and skips the host conversion.
+__global__ void __launch_bounds__(256) pcm16_to_mono_kernel(const int16_t* __restrict__ pcm, long long n_frames, int ch,
+                                                            float* __restrict__ out) {
+  const float n_ch = static_cast<float>(ch);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n_frames; i += 256ll * gridDim.x) {
+    float sum = 0.0f;
+    for (int c = 0; c < ch; ++c) sum += static_cast<float>(__ldg(pcm + i * ch + c)) * (1.0f / 32768.0f);
+    out[i] = ch == 1 ? sum : sum / n_ch;
+  }
+}
+
 }  // namespace amt
 
 extern "C" int amt_resample_poly_f32(const float* x, int64_t n_in, float* y, int64_t n_out, const float* taps,
@@ -66,6 +79,18 @@ extern "C" int amt_resample_poly_f32(const float* x, int64_t n_in, float* y, int
   AMT_REQUIRE(grid < (1ll << 31), "resample: output too long");
   resample_poly_kernel<<<static_cast<unsigned>(grid), kRsThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
       x, n_in, y, n_out, taps, n_taps, up, down, centre, static_cast<int>(span));
+  AMT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int amt_pcm16_to_mono_f32(const int16_t* pcm, int64_t n_frames, int channels, float* out, amt_stream_t stream_) {
+  using namespace amt;
+  AMT_REQUIRE(pcm && out && n_frames >= 0 && channels >= 1 && channels <= 64, "pcm16_to_mono: bad arguments");
+  AMT_TRY(ensure_device());
+  if (n_frames == 0) return 0;
+  const long long want = (n_frames + 256 * 4 - 1) / (256 * 4);
+  const int grid = static_cast<int>(want > 8ll * num_sms() ? 8ll * num_sms() : want);
+  pcm16_to_mono_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(pcm, n_frames, channels, out);
   AMT_CHECK_LAUNCH();
   return 0;
 }

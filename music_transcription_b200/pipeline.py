@@ -194,10 +194,16 @@ def pianoroll_to_midi(pianoroll, fs, min_midi=21) -> NoteList:
     return NoteList(extract_notes(roll, threshold=0.0), fs, min_midi)
 
 
-def split_audio_into_chunks(y: np.ndarray, chunk_length=CHUNK_LENGTH, sr=SR) -> List[np.ndarray]:
+def split_audio_into_chunks(y, chunk_length=CHUNK_LENGTH, sr=SR):
     """Chunking of an already-decoded mono signal (main.py:82-97): ceil(len/chunk) chunks, last one
-    zero-padded.  (Decoding/resampling, main.py:76, is a 'next' row: SURVEY.md section 8f.)"""
+    zero-padded.  A numpy signal gives the reference's list of arrays; a torch tensor (e.g. the CUDA output of
+    ``audio.load_audio``) gives one (n_chunks, chunk_samples) tensor on the same device -- no host round trip."""
     chunk_samples = int(chunk_length * sr)
+    if isinstance(y, torch.Tensor):
+        n = -(-y.numel() // chunk_samples)
+        out = torch.zeros(n * chunk_samples, dtype=y.dtype, device=y.device)
+        out[:y.numel()] = y.reshape(-1)
+        return out.view(n, chunk_samples)
     n = int(np.ceil(len(y) / chunk_samples))
     out = []
     for i in range(n):

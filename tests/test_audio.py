@@ -91,3 +91,43 @@ def test_transcribe_audio_writes_a_midi_file(tmp_path):
     notes = osmf.notes_from(parsed)
     assert all(21 <= p <= 108 and e > s for p, _, s, e in notes)
     assert max((e for *_, e in notes), default=0) <= round(2 * 938 / 31.25 * 440) + 1
+
+
+def test_pcm16_reader_and_tensor_chunk_split(tmp_path):
+    from scipy.io import wavfile
+    from music_transcription_b200 import pipeline
+    rng = np.random.default_rng(3)
+    pcm = rng.integers(-32768, 32767, size=(1000, 2), dtype=np.int16)
+    p = tmp_path / "s.wav"
+    wavfile.write(p, 22050, pcm)
+    raw, sr = audio.load_wav_pcm16(str(p))
+    assert sr == 22050 and raw.dtype == np.int16 and np.array_equal(raw, pcm)
+    x, _ = audio.load_wav(str(p))
+    assert np.array_equal(x, pcm.astype(np.float32) / 32768.0)
+    pf = tmp_path / "f.wav"
+    wavfile.write(pf, 16000, rng.standard_normal(100).astype(np.float32))
+    assert audio.load_wav_pcm16(str(pf)) is None                       # float WAVE: not the int16 fast path
+    # a torch signal is chunked exactly like the reference's numpy loop (main.py:82-97)
+    y = rng.standard_normal(2 * 480000 + 123).astype(np.float32)
+    ref = np.stack(pipeline.split_audio_into_chunks(y))
+    got = pipeline.split_audio_into_chunks(torch.from_numpy(y))
+    assert got.shape == (3, 480000) and np.array_equal(got.numpy(), ref)
+    assert pipeline.split_audio_into_chunks(torch.zeros(0)).shape == (0, 480000)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ch", [1, 2, 3])
+def test_pcm16_upload_path_is_bit_identical_to_host_decode(tmp_path, ch):
+    """load_audio uploads 16-bit PCM as int16 and converts / mixes on the GPU (amt_pcm16_to_mono_f32): the result must
+    equal the host float32 decode + numpy mean fed through the same resampler, bit for bit."""
+    from scipy.io import wavfile
+    rng = np.random.default_rng(ch)
+    pcm = rng.integers(-32768, 32767, size=(50001, ch), dtype=np.int16)
+    pcm[:4] = [[32767] * ch, [-32768] * ch, [0] * ch, [1] * ch]
+    p = tmp_path / "s.wav"
+    wavfile.write(p, 44100, pcm if ch > 1 else pcm[:, 0])
+    got, sr = audio.load_audio(str(p), device="cuda")
+    x, file_sr = audio.load_wav(str(p))
+    y = x.mean(axis=1, dtype=np.float32) if ch > 1 else x[:, 0]
+    want = audio.resample(y, file_sr, 16000, "cuda")
+    assert sr == 16000 and got.shape == want.shape and torch.equal(got, want)
