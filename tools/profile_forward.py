@@ -1,6 +1,7 @@
-"""Run the CNNRNNModelLarge forward (canonical config) a few times on B chunks of synthetic log-mel:
-the target of `ncu -k regex:tc_gemm` captures (12 tc_gemm launches per forward, in the order
-res1.c1, res1.c2, res2.c1, res2.c2, freq, rnn0.gemm, rnn1.gemm, rnn2.gemm, attn.qkv, attn.proj, fc1, heads)."""
+"""Run the CNNRNNModelLarge forward (canonical config) a few times on B chunks of synthetic log-mel: a small target for
+`ncu -k regex:<kernel>` captures of one kernel family (per forward: conv1, 5 conv_halo launches -- res1.c1, res1.c2,
+res2.c1, res2.c2, freq --, 7 tc_gemm launches -- rnn0/1/2.gemm, attn.qkv, attn.proj, fc1, heads --, 3 lstm_cluster,
+attention_tc, add_layernorm, heads_transpose)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
