@@ -92,5 +92,9 @@ def test_product_package_never_touches_the_oracle_or_the_reference_tree():
             if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "/root/reference" in src:
                 offenders.append(os.path.relpath(os.path.join(d, f), ROOT))
     assert offenders == []
+    for f in os.listdir(os.path.join(ROOT, "tools")):         # helper scripts are not a back door either
+        if f.endswith((".py", ".sh")) and not f.startswith("_"):
+            src = open(os.path.join(ROOT, "tools", f), errors="replace").read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) and "/root/reference" not in src, f
     for f in ("bench.py", "__graft_entry__.py"):          # nothing the GPU box runs may read the reference tree
         assert "/root/reference" not in open(os.path.join(ROOT, f)).read()
