@@ -127,6 +127,13 @@ int amt_bce_loss(const float* frame, const float* onset, const float* offset, co
 int amt_sigmoid_threshold(const float* logits, int64_t n, float thr, float* probs, float* roll,
                           amt_stream_t stream);
 
+/* Bit-packed roll: row r of vals [n_rows][T] (one pitch of one chunk) -> bits [n_rows][ceil(T/32)] uint32,
+ * bit (t % 32) of word (t / 32) = (v > thr) with v = sigmoid(vals) when apply_sigmoid != 0, else vals --
+ * the same float32 strict compare (and the same sigmoid) as amt_sigmoid_threshold, 1/32 of the bytes:
+ * what the streaming path downloads instead of the float roll of main.py:153-160. */
+int amt_pack_roll_u32(const float* vals, int64_t n_rows, int T, float thr, int apply_sigmoid, uint32_t* bits,
+                      amt_stream_t stream);
+
 /* Note grouping of reference main.py:204-223 on the roll formed by concatenating
  * `n_seg` segments along time (main.py:164-186):
  *   x[p][seg*T + t] = vals[seg*seg_stride + p*pitch_stride + t],  active iff x > thr
@@ -134,10 +141,14 @@ int amt_sigmoid_threshold(const float* logits, int64_t n, float thr, float* prob
  * Output rows (pitch_idx, onset_frame, offset_frame), pitch-major then onset
  * ascending.  notes: int32 [cap][3]; counts: int32 [n_pitch + 1] -- per-pitch
  * note counts and, last, the total (which may exceed cap: then only the first
- * `cap` rows were written).  scratch: int32 [n_pitch + 1] device. */
+ * `cap` rows were written).  scratch: device int32 [amt_threshold_notes_scratch_ints(n_seg, n_pitch)]
+ * (= 2 * n_seg * n_pitch: onset / offset counts per (pitch, segment)), owned by the caller like every
+ * other buffer -- the library keeps no device memory of its own, so calls on different devices,
+ * streams or host threads never share state.  Asynchronous. */
+size_t amt_threshold_notes_scratch_ints(int n_seg, int n_pitch);
 int amt_threshold_notes(const float* vals, int n_seg, int n_pitch, int T, int64_t seg_stride,
                         int64_t pitch_stride, float thr, int32_t* notes, int cap, int32_t* counts,
-                        amt_stream_t stream);
+                        int32_t* scratch, size_t scratch_ints, amt_stream_t stream);
 
 /* Framewise TP/FP/FN of reference scripts/evaluate.py:524-553 for every piece
  * and every threshold in one pass.  probs/target: [n_pieces][n_pitch][T_stride]

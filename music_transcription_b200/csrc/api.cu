@@ -1,4 +1,7 @@
 // Library plumbing: error strings, device checks, tensor-map encoding.
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace amt {
@@ -22,38 +25,75 @@ static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
-static int g_sms = 0;
-static int g_cc_major = -1;
+// Per-DEVICE caches: a process may drive several GPUs (one model / frontend handle per device), so nothing about
+// "the" device may be cached in a process-wide static.
+constexpr int kMaxDevices = 64;
+static int g_sms[kMaxDevices] = {0};
+static int g_cc_major[kMaxDevices] = {0};       // 0 = not queried yet
 
-static int query_device() {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
+static int current_device(int* dev) {
+  cudaError_t e = cudaGetDevice(dev);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(AMT_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
   }
-  cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, dev);
+  if (*dev < 0 || *dev >= kMaxDevices) return set_error(AMT_ERR_DEVICE, "device ordinal %d out of range", *dev);
+  return 0;
+}
+
+static int query_device(int dev) {
+  int sms = 0, major = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    return set_error(AMT_ERR_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return set_error(AMT_ERR_DEVICE, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
   }
-  g_sms = prop.multiProcessorCount;
-  g_cc_major = prop.major;
+  __atomic_store_n(&g_sms[dev], sms, __ATOMIC_RELAXED);
+  __atomic_store_n(&g_cc_major[dev], major, __ATOMIC_RELEASE);
   return 0;
 }
 
 int ensure_device() {
-  if (g_cc_major < 0) AMT_TRY(query_device());
-  if (g_cc_major != 10)
-    return set_error(AMT_ERR_DEVICE, "libamt_sm100 needs a compute-capability 10.x GPU (B200); found %d.x",
-                     g_cc_major);
+  int dev = 0;
+  AMT_TRY(current_device(&dev));
+  if (__atomic_load_n(&g_cc_major[dev], __ATOMIC_ACQUIRE) == 0) AMT_TRY(query_device(dev));
+  if (g_cc_major[dev] != 10)
+    return set_error(AMT_ERR_DEVICE, "libamt_sm100 needs a compute-capability 10.x GPU (B200); device %d is %d.x", dev,
+                     g_cc_major[dev]);
   return 0;
 }
 
 int num_sms() {
-  if (g_cc_major < 0) query_device();
-  return g_sms > 0 ? g_sms : 148;
+  int dev = 0;
+  if (current_device(&dev) != 0) return 148;
+  if (__atomic_load_n(&g_cc_major[dev], __ATOMIC_ACQUIRE) == 0 && query_device(dev) != 0) return 148;
+  return g_sms[dev] > 0 ? g_sms[dev] : 148;
+}
+
+struct AttrKey {
+  int dev;
+  const void* func;
+  int attr;
+  bool operator<(const AttrKey& o) const {
+    if (dev != o.dev) return dev < o.dev;
+    if (func != o.func) return func < o.func;
+    return attr < o.attr;
+  }
+};
+static std::mutex g_attr_mutex;
+static std::map<AttrKey, int> g_attr_values;
+
+int ensure_func_attr(const void* func, cudaFuncAttribute attr, int value) {
+  int dev = 0;
+  AMT_TRY(current_device(&dev));
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  const AttrKey key{dev, func, static_cast<int>(attr)};
+  auto it = g_attr_values.find(key);
+  if (it != g_attr_values.end() && it->second >= value) return 0;
+  AMT_CUDA(cudaFuncSetAttribute(func, attr, value));
+  g_attr_values[key] = value;
+  return 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -173,11 +173,7 @@ template <int HD>
 static int launch_attention(const void* qkv, void* out, int B, int T, int heads, float clip, cudaStream_t stream) {
   constexpr int PITCH = HD + 8;
   const int smem = (kQTile + 2 * kKTile) * PITCH * 2;
-  static bool attr = false;
-  if (!attr) {
-    AMT_CUDA(cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  AMT_FUNC_ATTR(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   dim3 grid(ceil_div(T, kQTile), heads, B);
   attention_kernel<HD><<<grid, 128, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
                                                      static_cast<__nv_bfloat16*>(out), T, heads,

@@ -420,11 +420,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 template <int HD>
 static int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, float clip, cudaStream_t stream) {
   using Cfg = AttCfg<HD>;
-  static bool attr = false;
-  if (!attr) {
-    AMT_CUDA(cudaFuncSetAttribute(attention_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr = true;
-  }
+  AMT_FUNC_ATTR(attention_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   const int D = heads * HD;
   CUtensorMap tq, tkv, to;
   {

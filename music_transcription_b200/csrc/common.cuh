@@ -52,8 +52,13 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 void count_launch();                  // every kernel launch of the library bumps amt_launch_count()
-int num_sms();                        // cached SM count of the current device
-int ensure_device();                  // AMT_ERR_DEVICE unless cc 10.x
+int num_sms();                        // SM count of the CURRENT device (cached per device)
+int ensure_device();                  // AMT_ERR_DEVICE unless the current device is cc 10.x
+// cudaFuncSetAttribute(func, attr, value) once per (device, func, attr) -- and again whenever a larger value is
+// needed: the opt-ins (dynamic shared memory above 48 KB, non-portable cluster sizes) are per-device state, so a
+// process that uses several GPUs must set them on each.  Thread-safe.
+int ensure_func_attr(const void* func, cudaFuncAttribute attr, int value);
+#define AMT_FUNC_ATTR(func, attr, value) AMT_TRY(amt::ensure_func_attr(reinterpret_cast<const void*>(func), attr, value))
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup, so the
 // library links without libcuda (it must load on CPU-only build hosts).

@@ -454,11 +454,7 @@ template <int KC, int BN, int KF>
 static int launch_conv_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
                             const CUtensorMap& o, const ConvHaloParams& p, cudaStream_t stream) {
   using Cfg = ConvHaloCfg<KC, BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AMT_CUDA(cudaFuncSetAttribute(conv_halo_kernel<KC, BN, KF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  AMT_FUNC_ATTR((conv_halo_kernel<KC, BN, KF>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   ConvHaloParams q = p;
   q.resident = (p.cblks * KF * 3 + p.cblks2 <= Cfg::kBStages) ? 1 : 0;
   if constexpr (Cfg::kPair) {

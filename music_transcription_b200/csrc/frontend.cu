@@ -375,11 +375,7 @@ int amt_logmel_f32(amt_frontend* fe, const float* wav, int B, int n_samples, int
   const size_t smem = sizeof(float) * ((span + 3) & ~3) + sizeof(float2) * kWarpsPerCta * 32 * 33 +
                       sizeof(float) * fe->n_mels * kFramesPerCta + sizeof(int) * (2 * fe->n_mels + 1) +
                       sizeof(float) * fe->dev.fb_nnz;
-  static size_t attr = 0;
-  if (smem > attr) {
-    AMT_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  AMT_FUNC_ATTR(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   fill_kernel<<<ceil_div(B, 256), 256, 0, stream>>>(chunk_max, B, -INFINITY);
   AMT_CHECK_LAUNCH();
   dim3 grid(ceil_div(T, kFramesPerCta), B);

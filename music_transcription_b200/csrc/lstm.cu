@@ -595,16 +595,8 @@ struct ClusterPlan {
 template <int BC>
 static int lstm_cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int grid, int CS, size_t smem,
                                cudaStream_t stream) {
-  static size_t attr_smem = 0;
-  static bool nonportable = false;
-  if (smem > attr_smem) {
-    AMT_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
-  if (CS > 8 && !nonportable) {
-    AMT_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<BC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    nonportable = true;
-  }
+  AMT_FUNC_ATTR(lstm_cluster_kernel<BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (CS > 8) AMT_FUNC_ATTR(lstm_cluster_kernel<BC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   *cfg = cudaLaunchConfig_t{};
   cfg->gridDim = dim3(grid);
   cfg->blockDim = dim3(kLstmThreads);
@@ -708,11 +700,7 @@ static int lstm_cluster_plan(const amt_lstm_seq* seqs, int n_seq, int B, Cluster
 
 template <int BC>
 static int lstm_launch(const LstmParams& p, int grid, size_t smem, cudaStream_t stream) {
-  static size_t attr = 0;
-  if (smem > attr) {
-    AMT_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  AMT_FUNC_ATTR(lstm_recurrence_kernel<BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   void* args[] = {const_cast<LstmParams*>(&p)};
   AMT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_recurrence_kernel<BC>), dim3(grid),
                                        dim3(kLstmThreads), args, smem, stream));

@@ -173,10 +173,16 @@ __global__ void __launch_bounds__(256) f1_counts_kernel(const float* __restrict_
 
 extern "C" {
 
+size_t amt_threshold_notes_scratch_ints(int n_seg, int n_pitch) {
+  if (n_seg < 1 || n_pitch < 1) return 0;
+  return 2 * static_cast<size_t>(n_seg) * static_cast<size_t>(n_pitch);
+}
+
 int amt_threshold_notes(const float* vals, int n_seg, int n_pitch, int T, int64_t seg_stride, int64_t pitch_stride,
-                        float thr, int32_t* notes, int cap, int32_t* counts, amt_stream_t stream_) {
+                        float thr, int32_t* notes, int cap, int32_t* counts, int32_t* scratch, size_t scratch_ints,
+                        amt_stream_t stream_) {
   using namespace amt;
-  AMT_REQUIRE(vals && notes && counts, "threshold_notes: NULL argument");
+  AMT_REQUIRE(vals && notes && counts && scratch, "threshold_notes: NULL argument");
   AMT_REQUIRE(n_seg >= 1 && n_pitch >= 1 && T >= 1 && cap >= 0, "threshold_notes: bad sizes");
   AMT_TRY(ensure_device());
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -184,21 +190,11 @@ int amt_threshold_notes(const float* vals, int n_seg, int n_pitch, int T, int64_
   AMT_REQUIRE(static_cast<long long>(n_seg) * T < (1ll << 31), "threshold_notes: roll too long");
   RollView rv{vals, n_seg, T, seg_stride, pitch_stride, thr};
   const int n = n_pitch * n_seg;
-  // per-(pitch, segment) onset / offset counts -> ranks.  Library-owned scratch, grown on demand and reused
-  // (stream-ordered within one stream; like the handles, not for concurrent calls from several host threads)
-  static int32_t* scratch = nullptr;
-  static size_t scratch_ints = 0;
-  if (scratch_ints < 2 * static_cast<size_t>(n)) {
-    if (scratch) {
-      AMT_CUDA(cudaDeviceSynchronize());
-      AMT_CUDA(cudaFree(scratch));
-      scratch = nullptr;
-      scratch_ints = 0;
-    }
-    const size_t want = std::max<size_t>(2 * static_cast<size_t>(n), 1 << 16);
-    AMT_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), sizeof(int32_t) * want));
-    scratch_ints = want;
-  }
+  // per-(pitch, segment) onset / offset counts -> ranks, in CALLER scratch (the library owns no device memory:
+  // nothing here is tied to one device, one stream or one host thread, and the call is graph-capturable)
+  if (scratch_ints < 2 * static_cast<size_t>(n))
+    return set_error(AMT_ERR_WORKSPACE, "threshold_notes: scratch of %zu ints < %zu (amt_threshold_notes_scratch_ints)",
+                     scratch_ints, 2 * static_cast<size_t>(n));
   const int grid = ceil_div(n, 8);
   notes_scan_kernel<false><<<grid, 256, 0, stream>>>(rv, n_pitch, scratch, scratch + n, notes, cap);
   AMT_CHECK_LAUNCH();
@@ -220,7 +216,7 @@ int amt_f1_counts(const float* probs, const float* target, const int32_t* length
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   AMT_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t) * 3 * static_cast<size_t>(n_pieces) * n_thr, stream));
   const size_t smem = sizeof(uint32_t) * 8 * 2 * (n_thr + 1) + sizeof(float) * n_thr;
-  if (smem > 48 * 1024) AMT_CUDA(cudaFuncSetAttribute(f1_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) AMT_FUNC_ATTR(f1_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const long long cells = static_cast<long long>(n_pitch) * T_stride;
   int bx = static_cast<int>(std::min<long long>((cells + 256 * 8 - 1) / (256 * 8), 64));
   if (bx < 1) bx = 1;

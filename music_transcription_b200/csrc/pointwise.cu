@@ -1,5 +1,7 @@
 // HBM-bound kernels around the GEMMs: the Cin=1 stem convolution, residual+LayerNorm,
 // head finalisation (transpose to (B,88,T)) and sigmoid/threshold.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace amt {
@@ -187,13 +189,37 @@ int run_heads_transpose(const float* in, int ld, int B, int T, int n_heads, floa
 // ----------------------------------------------------------------------------
 // probs = sigmoid(logits); roll = probs > thr  (reference main.py:153-156)
 // ----------------------------------------------------------------------------
+// ONE definition of the probability for every kernel that thresholds, so the float roll, the bit-packed roll
+// and the note grouper can never disagree on a cell
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
 __global__ void sigmoid_threshold_kernel(const float* __restrict__ logits, long long n, float thr, float* __restrict__ probs,
                                          float* __restrict__ roll) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float p = 1.0f / (1.0f + expf(-logits[i]));
+    const float p = sigmoid_ref(logits[i]);
     if (probs) probs[i] = p;
     if (roll) roll[i] = p > thr ? 1.0f : 0.0f;
+  }
+}
+
+// Bit-packed piano roll: row r (one pitch of one chunk, T frames) -> ceil(T/32) little-endian words, bit t%32 of
+// word t/32 = (value > thr).  A warp ballots 32 frames into one word: 88 x 938 floats (330 KB) become 10.6 KB per
+// chunk, which is what leaves the device in the streaming path ("bit-packed rolls").
+__global__ void __launch_bounds__(256) pack_roll_kernel(const float* __restrict__ vals, long long n_rows, int T, int words,
+                                                        float thr, int apply_sigmoid, uint32_t* __restrict__ bits) {
+  const int lane = threadIdx.x & 31;
+  const long long n_words = n_rows * words;
+  for (long long w = blockIdx.x * 8ll + (threadIdx.x >> 5); w < n_words; w += gridDim.x * 8ll) {
+    const long long row = w / words;
+    const int t = static_cast<int>(w - row * words) * 32 + lane;
+    bool on = false;
+    if (t < T) {
+      const float x = __ldg(vals + row * T + t);
+      on = (apply_sigmoid ? sigmoid_ref(x) : x) > thr;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) bits[w] = m;
   }
 }
 
@@ -205,8 +231,23 @@ extern "C" int amt_sigmoid_threshold(const float* logits, int64_t n, float thr, 
   AMT_REQUIRE(logits && n >= 0, "sigmoid_threshold: bad arguments");
   AMT_TRY(ensure_device());
   if (n == 0) return 0;
-  const long long blocks = std::min<long long>((n + 255) / 256, 148ll * 8);
+  const long long blocks = std::min<long long>((n + 255) / 256, 8ll * num_sms());
   sigmoid_threshold_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, n, thr, probs, roll);
+  AMT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int amt_pack_roll_u32(const float* vals, int64_t n_rows, int T, float thr, int apply_sigmoid, uint32_t* bits,
+                                 amt_stream_t stream) {
+  using namespace amt;
+  AMT_REQUIRE(vals && bits && n_rows >= 0 && T >= 1, "pack_roll: bad arguments");
+  AMT_TRY(ensure_device());
+  if (n_rows == 0) return 0;
+  const int words = (T + 31) / 32;
+  const long long n_words = n_rows * words;
+  const long long blocks = std::min<long long>((n_words + 7) / 8, 16ll * num_sms());
+  pack_roll_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(vals, n_rows, T, words, thr,
+                                                                                               apply_sigmoid, bits);
   AMT_CHECK_LAUNCH();
   return 0;
 }

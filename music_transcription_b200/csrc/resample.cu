@@ -70,11 +70,7 @@ extern "C" int amt_resample_poly_f32(const float* x, int64_t n_in, float* y, int
   const long long span = (static_cast<long long>(kRsTile - 1) * down + up - 1) / up + taps_per_phase + 2;
   AMT_REQUIRE(span * 4 <= 200 * 1024, "resample: ratio %d/%d with %d taps needs too large an input tile", up, down, n_taps);
   const size_t smem = static_cast<size_t>(span) * 4;
-  static size_t attr = 0;
-  if (smem > attr && smem > 48 * 1024) {
-    AMT_CUDA(cudaFuncSetAttribute(resample_poly_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  if (smem > 48 * 1024) AMT_FUNC_ATTR(resample_poly_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const long long grid = (n_out + kRsTile - 1) / kRsTile;
   AMT_REQUIRE(grid < (1ll << 31), "resample: output too long");
   resample_poly_kernel<<<static_cast<unsigned>(grid), kRsThreads, smem, static_cast<cudaStream_t>(stream_)>>>(

@@ -268,12 +268,7 @@ template <int BN, bool OUT_F32>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmParams& p,
                   cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AMT_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  AMT_FUNC_ATTR((tc_gemm_kernel<BN, OUT_F32>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   const int pairs = p.num_tiles < num_sms() / 2 ? p.num_tiles : num_sms() / 2;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];

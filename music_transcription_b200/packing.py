@@ -71,14 +71,14 @@ def _feat_perm_cols(w: torch.Tensor, C: int, F: int) -> torch.Tensor:
 
 def pack_state_dict(sd: Dict[str, torch.Tensor], model_type: str, n_mels: int, hidden_size: int, num_layers: int,
                     use_attention: bool = True, use_onset_offset_heads: bool = True,
-                    device=None) -> Dict[str, torch.Tensor]:
+                    device=None, weight_dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
     mt = model_type.lower()
     large = mt in ("cnn_rnn_large", "large")
     if not large and mt not in ("cnn_rnn", "cnn+rnn"):
         raise ValueError(f"Unknown model type: {model_type}")
     H = hidden_size
     out: Dict[str, torch.Tensor] = {}
-    bf = torch.bfloat16
+    bf = weight_dtype          # bf16 for the kernels; tests/attribution.py packs fp32 to isolate rounding steps
 
     def put(name, t, dtype):
         t = t.to(dtype).contiguous()

@@ -164,26 +164,32 @@ def extract_notes(vals: torch.Tensor, threshold: float = 0.0, cap: int | None = 
         cap = n_pitch * ((n_seg * T + 1) // 2)          # the most notes a roll of that size can hold
     notes = torch.empty(max(cap, 1), 3, dtype=torch.int32, device=dev)
     counts = torch.empty(n_pitch + 1, dtype=torch.int32, device=dev)
+    scratch = torch.empty(2 * n_seg * n_pitch, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().amt_threshold_notes(_lib.ptr(vals), n_seg, n_pitch, T, vals.stride(0), vals.stride(1),
                                                   float(np.float32(threshold)), _lib.ptr(notes), cap, _lib.ptr(counts),
-                                                  _lib.stream_ptr(dev)))
+                                                  _lib.ptr(scratch), scratch.numel(), _lib.stream_ptr(dev)))
     total = int(counts[n_pitch].item())
     if total > cap:
         raise _lib.AmtError(f"extract_notes: {total} notes exceed cap {cap}")
     return notes[:total].cpu().numpy()
 
 
-def extract_notes_async(vals: torch.Tensor, threshold: float, notes_out: torch.Tensor, counts_out: torch.Tensor) -> None:
+def extract_notes_async(vals: torch.Tensor, threshold: float, notes_out: torch.Tensor, counts_out: torch.Tensor,
+                        scratch: torch.Tensor | None = None) -> None:
     """Launch-only variant of ``extract_notes`` (no host sync): writes int32 triples into ``notes_out``
-    (cap = notes_out.shape[0]) and per-pitch counts + total into ``counts_out`` (n_pitch + 1)."""
+    (cap = notes_out.shape[0]) and per-pitch counts + total into ``counts_out`` (n_pitch + 1).  ``scratch``:
+    int32 device tensor of at least 2 * n_seg * n_pitch elements (allocated from torch's caching allocator when None)."""
     if vals.dim() == 2:
         vals = vals[None]
     n_seg, n_pitch, T = vals.shape
+    if scratch is None:
+        scratch = torch.empty(2 * n_seg * n_pitch, dtype=torch.int32, device=vals.device)
     with torch.cuda.device(vals.device):
         _lib.check(_lib.lib().amt_threshold_notes(_lib.ptr(vals), n_seg, n_pitch, T, vals.stride(0), vals.stride(1),
                                                   float(np.float32(threshold)), _lib.ptr(notes_out), notes_out.shape[0],
-                                                  _lib.ptr(counts_out), _lib.stream_ptr(vals.device)))
+                                                  _lib.ptr(counts_out), _lib.ptr(scratch), scratch.numel(),
+                                                  _lib.stream_ptr(vals.device)))
 
 
 def pianoroll_to_midi(pianoroll, fs, min_midi=21) -> NoteList:
@@ -236,15 +242,49 @@ def transcribe_chunks(model, wav: torch.Tensor, threshold: float = THRESHOLD, sr
     return notes, (probs if return_probs else None)
 
 
+def pack_roll(vals: torch.Tensor, threshold: float, apply_sigmoid: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(..., T) float32 CUDA (probabilities, or logits with ``apply_sigmoid``) -> (..., ceil(T/32)) int32 words holding
+    bit t%32 of word t/32 = (value > float32(threshold)): the piano roll at 1/32 of the float bytes."""
+    _lib.require_cuda(vals, "pack_roll input")
+    vals = vals.float().contiguous()
+    T = vals.shape[-1]
+    words = (T + 31) // 32
+    if out is None:
+        out = torch.empty(*vals.shape[:-1], words, dtype=torch.int32, device=vals.device)
+    with torch.cuda.device(vals.device):
+        _lib.check(_lib.lib().amt_pack_roll_u32(_lib.ptr(vals), vals.numel() // T, T, float(np.float32(threshold)),
+                                                int(apply_sigmoid), _lib.ptr(out), _lib.stream_ptr(vals.device)))
+    return out
+
+
+def unpack_roll(bits, T: int) -> np.ndarray:
+    """Host-side inverse of ``pack_roll``: (..., ceil(T/32)) int32 words (tensor or array) -> (..., T) float32 {0,1},
+    the array ``predict_chunk`` returns (main.py:153-160)."""
+    a = bits.cpu().numpy() if torch.is_tensor(bits) else np.asarray(bits)
+    a = np.ascontiguousarray(a).view(np.uint32)
+    b = np.unpackbits(a.view(np.uint8).reshape(*a.shape[:-1], -1), axis=-1, bitorder="little")
+    return b[..., :T].astype(np.float32)
+
+
 class StreamingTranscriber:
     """Host buffers in, host piano-rolls + note lists out, batch after batch, with the copies of batch i+1
     (pinned host audio -> device) and of batch i-1 (rolls and notes -> pinned host) overlapped with the compute
     of batch i: three CUDA streams, two buffer slots.  This is the end-to-end form of main.py:258-275 for a
     long recording -- every batch still pays its H2D and D2H, they just no longer sit on the critical path.
 
-        st = StreamingTranscriber(model, chunks_per_batch=64)
-        for roll, notes in st.run(pinned_batches):      # roll: pinned (C, 88, T) float {0,1}; notes: (n, 3) int32
-            ...
+        st = StreamingTranscriber(model, chunks_per_batch=64, input_format="pcm16")
+        for roll_bits, notes in st.run(pinned_batches):
+            roll = unpack_roll(roll_bits, st.T)         # (C, 88, T) float32 {0,1}; notes: (n, 3) int32
+
+    ``input_format``: "f32" -- pinned float32 (c, n_samples) batches, what ``librosa.load`` hands main.py:76;
+        "pcm16" -- pinned int16 (c, n_samples) mono PCM as a 16-bit WAVE file stores it: half the PCIe bytes, converted
+        on the device by ``amt_pcm16_to_mono_f32`` (sample / 32768, bit-identical to the host decode).
+    ``roll_format``: "bits" (default) -- the roll leaves the device bit-packed, int32 (c, 88, ceil(T/32)),
+        10.6 KB instead of 330 KB per chunk (``unpack_roll`` restores the float array); "f32" -- the float {0,1} roll
+        of main.py:153-160 itself.
+    LIFETIME: each yielded (roll, notes) pair is a VIEW into one of two reused pinned slots and is valid until the
+    next-but-one batch is launched, i.e. until the generator is advanced again -- consume or copy it inside the loop
+    body (``copy=True`` yields private copies instead, for ``list(st.run(...))``).
     ``notes`` are grouped per batch (frame indices relative to the batch); ``sharding.stitch_notes`` merges
     batches / ranks exactly like grouping the concatenated roll."""
 
@@ -252,50 +292,75 @@ class StreamingTranscriber:
         pass
 
     def __init__(self, model, chunks_per_batch: int, n_samples: int = int(CHUNK_LENGTH * SR), threshold: float = THRESHOLD,
-                 sr=SR, n_mels=N_MELS, hop_length=HOP_LENGTH):
+                 sr=SR, n_mels=N_MELS, hop_length=HOP_LENGTH, input_format: str = "f32", roll_format: str = "bits",
+                 copy: bool = False):
+        if input_format not in ("f32", "pcm16") or roll_format not in ("bits", "f32"):
+            raise ValueError("StreamingTranscriber: input_format in {'f32','pcm16'}, roll_format in {'bits','f32'}")
         self.model, self.C, self.thr = model, chunks_per_batch, float(threshold)
+        self.input_format, self.roll_format, self.copy = input_format, roll_format, copy
         dev = torch.device(model.device)
         _lib.require_cuda(torch.empty(0, device=dev), "StreamingTranscriber device")
         self.dev = dev
         self.fe = Frontend.get(sr, n_mels, hop_length, dev)
         self.T = self.fe.num_frames(n_samples)
+        self.n_samples = n_samples
         C, T = chunks_per_batch, self.T
+        W = (T + 31) // 32
         cap = 88 * ((C * T + 1) // 2)
         self.copy_in, self.copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.slots = []
         for _ in range(2):
             s = StreamingTranscriber._Slot()
             s.wav = torch.empty(C, n_samples, device=dev)
+            s.pcm = torch.empty(C, n_samples, dtype=torch.int16, device=dev) if input_format == "pcm16" else None
             s.probs = torch.empty(C, 88, T, device=dev)
-            s.roll = torch.empty(C, 88, T, device=dev)
+            if roll_format == "f32":
+                s.roll = torch.empty(C, 88, T, device=dev)
+                s.host_roll = torch.empty(C, 88, T, dtype=torch.float32).pin_memory()
+            else:
+                s.roll = torch.empty(C, 88, W, dtype=torch.int32, device=dev)
+                s.host_roll = torch.empty(C, 88, W, dtype=torch.int32).pin_memory()
             s.notes = torch.empty(cap, 3, dtype=torch.int32, device=dev)
             s.counts = torch.zeros(89, dtype=torch.int32, device=dev)
-            s.host_roll = torch.empty(C, 88, T, dtype=torch.float32).pin_memory()
+            s.scratch = torch.empty(2 * 88 * C, dtype=torch.int32, device=dev)
             s.host_counts = torch.zeros(89, dtype=torch.int32).pin_memory()
             s.host_notes = torch.empty(cap, 3, dtype=torch.int32).pin_memory()
             s.h2d_done, s.compute_done, s.counts_done, s.d2h_done = (torch.cuda.Event() for _ in range(4))
             s.n = C
             self.slots.append(s)
-        self.h2d_bytes = C * n_samples * 4
-        self.roll_bytes = C * 88 * T * 4 + 89 * 4
+        self.h2d_bytes = C * n_samples * (2 if input_format == "pcm16" else 4)
+        self.roll_bytes = s.host_roll.numel() * 4 + 89 * 4
 
     def _launch(self, i: int, host_wav: torch.Tensor) -> None:
         s = self.slots[i & 1]
         compute = torch.cuda.current_stream(self.dev)
         n = host_wav.shape[0]
+        want = torch.int16 if self.input_format == "pcm16" else torch.float32
+        if host_wav.dtype != want or host_wav.shape[1] != self.n_samples or n > self.C:
+            raise ValueError(f"StreamingTranscriber: expected {want} batches of shape (<= {self.C}, {self.n_samples}), "
+                             f"got {host_wav.dtype} {tuple(host_wav.shape)}")
         s.n = n
+        L = _lib.lib()
         with torch.cuda.stream(self.copy_in):
             self.copy_in.wait_event(s.compute_done)             # the compute that last read this slot's audio is done
-            s.wav[:n].copy_(host_wav, non_blocking=True)
+            (s.pcm if s.pcm is not None else s.wav)[:n].copy_(host_wav, non_blocking=True)
             s.h2d_done.record(self.copy_in)
         compute.wait_event(s.h2d_done)
         compute.wait_event(s.d2h_done)                          # this slot's previous results have left the device
-        mel = self.fe.logmel(s.wav[:n])
-        logits = self.model(mel)
         with torch.cuda.device(self.dev):
-            _lib.check(_lib.lib().amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), self.thr, _lib.ptr(s.probs),
-                                                        _lib.ptr(s.roll), _lib.stream_ptr(self.dev)))
-        extract_notes_async(s.probs[:n], self.thr, s.notes, s.counts)
+            if s.pcm is not None:
+                _lib.check(L.amt_pcm16_to_mono_f32(_lib.ptr(s.pcm), n * self.n_samples, 1, _lib.ptr(s.wav), _lib.stream_ptr(self.dev)))
+            mel = self.fe.logmel(s.wav[:n])
+            logits = self.model(mel)
+            if self.roll_format == "f32":
+                _lib.check(L.amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), self.thr, _lib.ptr(s.probs),
+                                                   _lib.ptr(s.roll), _lib.stream_ptr(self.dev)))
+            else:
+                _lib.check(L.amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), self.thr, _lib.ptr(s.probs), 0,
+                                                   _lib.stream_ptr(self.dev)))
+                _lib.check(L.amt_pack_roll_u32(_lib.ptr(s.probs), n * 88, self.T, self.thr, 0, _lib.ptr(s.roll),
+                                               _lib.stream_ptr(self.dev)))
+        extract_notes_async(s.probs[:n], self.thr, s.notes, s.counts, s.scratch)
         s.compute_done.record(compute)
         with torch.cuda.stream(self.copy_out):
             self.copy_out.wait_event(s.compute_done)
@@ -313,10 +378,12 @@ class StreamingTranscriber:
             s.host_notes[:total].copy_(s.notes[:total], non_blocking=True)
             s.d2h_done.record(self.copy_out)
         s.d2h_done.synchronize()
-        return s.host_roll[:s.n], s.host_notes[:total].numpy()
+        roll, notes = s.host_roll[:s.n], s.host_notes[:total].numpy()
+        return (roll.clone(), notes.copy()) if self.copy else (roll, notes)
 
     def run(self, host_batches):
-        """host_batches: iterable of pinned float32 (c <= chunks_per_batch, n_samples) tensors."""
+        """host_batches: iterable of pinned (c <= chunks_per_batch, n_samples) tensors, float32 or int16 per
+        ``input_format``.  Yields (roll, notes) per batch -- see the class docstring for formats and lifetime."""
         i = -1
         for i, hb in enumerate(host_batches):
             self._launch(i, hb)

@@ -91,6 +91,41 @@ def gen_models():
     np.savez_compressed(os.path.join(OUT, "model_T0.npz"), raised=np.array(raised))
 
 
+CANON = dict(n_mels=320, hidden=512, layers=3, T=938, seed=1, gain=3 ** -0.5)
+
+
+def canon_input(ks):
+    """The canonical-shape fixture input: log-mel of the SURVEY 8(d) chord chunks (oracle frontend), rounded to the
+    float16 grid so the fixture stores it exactly in half the bytes.  (B,1,320,938) float32."""
+    from oracle import frontend as fe
+    x = np.stack([fe.logmel(synth.piano_chord(int(k))) for k in ks])[:, None]
+    return torch.from_numpy(x.astype(np.float16).astype(np.float32))
+
+
+def gen_canonical():
+    """Reference-run fixtures AT THE CANONICAL SHAPES (main.py:16-24: n_mels 320, hidden 512, 3 layers, T 938), so the
+    16-CTA-cluster LSTM (H = 512 / 256), the head-dim-192 attention and the K = 10240 projection are pinned by the real
+    reference modules, not only by the port: CNNRNNModelLarge on 2 chord chunks (three heads) and CNNRNNModel (36 M) on 1."""
+    TM = _ref_modules()
+    c = CANON
+    for name, mt, ks in (("large", "cnn_rnn_large", [0, 3]), ("small", "cnn_rnn", [0])):
+        sd = synth.synth_state_dict(mt, c["n_mels"], c["hidden"], c["layers"], seed=c["seed"], gain=c["gain"])
+        m = TM(model_type=mt, n_mels=c["n_mels"], hidden_size=c["hidden"], num_layers=c["layers"], dropout=0.2, device="cpu")
+        m.load_state_dict(sd, strict=True)
+        m.eval()
+        x = canon_input(ks)
+        with torch.no_grad():
+            out = {"frame": m(x).numpy()}
+            if mt.endswith("large"):
+                allh = m(x, return_all_heads=True)
+                assert np.array_equal(allh["frame"].numpy(), out["frame"])
+                out["onset"], out["offset"] = allh["onset"].numpy(), allh["offset"].numpy()
+        np.savez_compressed(os.path.join(OUT, f"canon_{name}.npz"), model_type=mt, chunks=np.array(ks),
+                            cfg=np.array([c["n_mels"], c["hidden"], c["layers"], len(ks), c["T"], c["seed"]]),
+                            gain=np.float64(c["gain"]), x=x.numpy().astype(np.float16), **out)
+        print("canonical", name, out["frame"].shape, "logit std", float(out["frame"].std()))
+
+
 class _FakeNote:
     def __init__(self, velocity, pitch, start, end):
         self.velocity, self.pitch, self.start, self.end = velocity, pitch, start, end
@@ -286,7 +321,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "losses":
         gen_losses()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "canonical":
+        torch.set_num_threads(os.cpu_count() or 4)
+        gen_canonical()
+        sys.exit(0)
     gen_models()
+    gen_canonical()
     gen_losses()
     gen_notes()
     gen_f1()

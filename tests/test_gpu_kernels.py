@@ -275,3 +275,32 @@ def test_sigmoid_threshold_strict_compare():
     _lib.check(_lib.lib().amt_sigmoid_threshold(_lib.ptr(x), 4, 0.5, _lib.ptr(probs), _lib.ptr(roll), _stream()))
     assert roll.tolist() == [0.0, 0.0, 1.0, 0.0]          # sigmoid(0) == 0.5 is NOT > 0.5
     assert torch.allclose(probs, torch.sigmoid(x), atol=1e-7)
+
+
+def test_pack_roll_bits_equal_float_roll():
+    """amt_pack_roll_u32: bit t%32 of word t/32 == the float roll of amt_sigmoid_threshold, for probabilities and for
+    logits (same sigmoid), ragged T (not a multiple of 32), values planted exactly on float32(threshold)."""
+    from music_transcription_b200 import pipeline
+    for T, thr in ((938, 0.5), (33, 0.35000000000000003), (1, 0.5), (64, 0.1)):
+        p = torch.from_numpy(synth.planted_probs(88 * 3, T, [thr], seed=T, frac=0.05)).to(DEV).view(3, 88, T)
+        bits = pipeline.pack_roll(p, thr)
+        assert bits.shape == (3, 88, (T + 31) // 32) and bits.dtype == torch.int32
+        want = (p > float(np.float32(thr))).float().cpu().numpy()
+        assert np.array_equal(pipeline.unpack_roll(bits, T), want)
+        logits = torch.randn(2, 88, T, device=DEV) * 3
+        logits[0, 0, 0] = 0.0                                 # sigmoid(0) == 0.5 is not > 0.5
+        roll = torch.empty_like(logits)
+        _lib.check(_lib.lib().amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), 0.5, 0, _lib.ptr(roll), _stream()))
+        assert np.array_equal(pipeline.unpack_roll(pipeline.pack_roll(logits, 0.5, apply_sigmoid=True), T), roll.cpu().numpy())
+
+
+def test_threshold_notes_takes_caller_scratch_and_rejects_a_short_one():
+    L = _lib.lib()
+    assert L.amt_threshold_notes_scratch_ints(3, 88) == 2 * 3 * 88
+    p = torch.rand(3, 88, 50, device=DEV)
+    notes = torch.empty(88 * 75, 3, dtype=torch.int32, device=DEV)
+    counts = torch.empty(89, dtype=torch.int32, device=DEV)
+    scratch = torch.empty(2 * 3 * 88 - 1, dtype=torch.int32, device=DEV)
+    st = L.amt_threshold_notes(_lib.ptr(p), 3, 88, 50, p.stride(0), p.stride(1), 0.5, _lib.ptr(notes), notes.shape[0],
+                               _lib.ptr(counts), _lib.ptr(scratch), scratch.numel(), _stream())
+    assert st == _lib.AMT_ERR_WORKSPACE and b"scratch" in L.amt_last_error()

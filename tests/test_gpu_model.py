@@ -216,6 +216,94 @@ def test_canonical_large_model_vs_oracle_full_chunk():
     assert (solo[0] - out["frame"][1]).abs().max() < 1e-5
 
 
+def _report(name, **vals):
+    """Measured parity numbers -> gpurun_out/parity_report.jsonl (scratch; summarised under profiles/ by hand)."""
+    import json
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: float(v) for k, v in vals.items()}}) + "\n")
+
+
+CANON_PROB_MAX, CANON_PROB_MEAN, CANON_FLIPS = 4e-3, 6e-4, 5e-3      # fast (bf16) mode; measured values in profiles/r2_parity.md
+
+
+@pytest.mark.parametrize("name", ["large", "small"])
+def test_canonical_shape_goldens_from_the_real_reference(name):
+    """tests/golden/canon_*.npz: outputs of the UNMODIFIED reference modules at the canonical shapes (n_mels 320,
+    hidden 512, 3 layers, T 938: the 16-CTA-cluster LSTM, head-dim-192 attention, K = 10240 projection) on chord
+    log-mel.  CNNRNNModelLarge (three heads, 2 chunks) and CNNRNNModel 36 M (BASELINE configs[0]'s model)."""
+    g = np.load(os.path.join(GOLDEN, f"canon_{name}.npz"))
+    n_mels, H, L, B, T, seed = [int(v) for v in g["cfg"]]
+    mt = str(g["model_type"])
+    sd = synth.synth_state_dict(mt, n_mels, H, L, seed=seed, gain=float(g["gain"]))
+    m = TranscriptionModel(mt, n_mels=n_mels, hidden_size=H, num_layers=L, dropout=0.2, device=DEV)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x = torch.from_numpy(g["x"].astype(np.float32)).to(DEV)
+    out = m(x, return_all_heads=True)
+    out = out if isinstance(out, dict) else {"frame": out}
+    assert sorted(out) == (["frame", "offset", "onset"] if name == "large" else ["frame"])
+    for k, v in out.items():
+        ref = torch.from_numpy(g[k])
+        assert v.shape == ref.shape == (B, 88, T)
+        dp = (torch.sigmoid(v.cpu()) - torch.sigmoid(ref)).abs()
+        flips = ((v.cpu() > 0) != (ref > 0)).float().mean()
+        _report(f"canon_{name}.{k}", prob_max=dp.max(), prob_mean=dp.mean(), logit_max=(v.cpu() - ref).abs().max(), flips=flips)
+        assert dp.max() < CANON_PROB_MAX and dp.mean() < CANON_PROB_MEAN and flips < CANON_FLIPS, (k, dp.max(), dp.mean(), flips)
+
+
+@pytest.mark.parametrize("B", [16, 64])
+def test_large_model_batch_16_and_64_invariance_and_oracle(B):
+    """BASELINE configs[2] (batch 16) and the bench batch (64) on the north-star model: every chunk's logits are
+    bitwise what the same chunk gives alone (B = 1), and 4 of the chunks agree with the fp32 oracle."""
+    from oracle import model as omodel
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    sd = synth.synth_state_dict("cnn_rnn_large", 320, 512, 3, seed=1, gain=3 ** -0.5)
+    m = TranscriptionModel("cnn_rnn_large", n_mels=320, hidden_size=512, num_layers=3, dropout=0.2, device=DEV)
+    m.load_state_dict(sd)
+    wav = torch.from_numpy(synth.piano_chord_batch(range(16))).to(DEV)
+    if B > 16:
+        wav = torch.cat([wav * (1.0 - 0.05 * j) for j in range(B // 16)])
+    mel = pipeline.Frontend.get(device=DEV).logmel(wav)
+    out = m(mel, return_all_heads=True)
+    picks = [0, 5, B // 2 + 1, B - 1]
+    for i in picks:
+        solo = m(mel[i:i + 1], return_all_heads=True)
+        for k in ("frame", "onset", "offset"):
+            assert torch.equal(solo[k][0], out[k][i]), (B, i, k, (solo[k][0] - out[k][i]).abs().max().item())
+    ref = omodel.large_forward(sd, mel[picks].cpu(), 512, 3, return_all_heads=True)
+    for k in ("frame", "onset", "offset"):
+        dp = (torch.sigmoid(out[k][picks].cpu()) - torch.sigmoid(ref[k])).abs()
+        _report(f"large_B{B}.{k}", prob_max=dp.max(), prob_mean=dp.mean())
+        assert dp.max() < CANON_PROB_MAX and dp.mean() < CANON_PROB_MEAN, (B, k, dp.max(), dp.mean())
+
+
+def test_two_hour_recording_240_chunks_on_the_large_model():
+    """BASELINE configs[3] on the north-star model: 240 x 30-s chunks through CNNRNNModelLarge (320/512/3).  The
+    oracle cannot run at this size, so: (i) the note list does not depend on the batching (240 at once vs 64-chunk
+    batches), (ii) it equals the oracle's grouping of the SAME GPU probability roll, seams included, (iii) a chunk's
+    logits are bitwise independent of its batch and position."""
+    from oracle import notes as onotes
+    sd = synth.synth_state_dict("cnn_rnn_large", 320, 512, 3, seed=1, gain=3 ** -0.5)
+    m = TranscriptionModel("cnn_rnn_large", n_mels=320, hidden_size=512, num_layers=3, dropout=0.2, device=DEV)
+    m.load_state_dict(sd)
+    base = synth.cheap_wave_batch(8, 480000, seed=7)
+    wav = torch.empty(240, 480000, device=DEV)
+    for i in range(240):
+        wav[i] = base[i % 8].to(DEV) * (1.0 - 0.003 * (i // 8))
+    notes_a, probs = pipeline.transcribe_chunks(m, wav, threshold=0.5, batch=240, return_probs=True)
+    notes_b, _ = pipeline.transcribe_chunks(m, wav, threshold=0.5, batch=64)
+    assert len(notes_a) > 0 and np.array_equal(notes_a, notes_b)
+    p = probs.cpu().numpy()
+    want = onotes.group_notes(onotes.combine_piano_rolls([onotes.threshold_roll(p[i], 0.5) for i in range(240)]))
+    assert np.array_equal(notes_a, want)
+    fe = pipeline.Frontend.get(device=DEV)
+    solo = m(fe.logmel(wav[100:101]))
+    batch = m(fe.logmel(wav[96:112]))
+    assert torch.equal(solo[0], batch[4])
+
+
 def test_transcribe_chunks_end_to_end_notes_match_oracle_on_same_probs():
     from oracle import notes as onotes
     sd = synth.synth_state_dict("cnn_rnn", 320, 128, 1, seed=2, gain=2.0)
@@ -256,18 +344,36 @@ def test_two_hour_recording_240_chunks_batch_invariance_and_notes():
     assert torch.equal(solo[0], batch[4])
 
 
-def test_streaming_transcriber_equals_batch_by_batch_path():
+@pytest.mark.parametrize("input_format,roll_format", [("f32", "f32"), ("pcm16", "bits"), ("f32", "bits")])
+def test_streaming_transcriber_equals_batch_by_batch_path(input_format, roll_format):
     """Overlapped H2D / compute / D2H (3 streams, 2 slots) must return exactly what the plain per-batch path does,
-    including a short last batch and slot reuse (5 batches over 2 slots)."""
+    including a short last batch and slot reuse (5 batches over 2 slots) -- for float32 and 16-bit PCM input (the
+    on-device conversion is bit-identical to sample / 32768 on the host) and for the float and the bit-packed roll."""
     sd = synth.synth_state_dict("cnn_rnn", 320, 128, 1, seed=5, gain=2.0)
     m = TranscriptionModel("cnn_rnn", n_mels=320, hidden_size=128, num_layers=1, device=DEV)
     m.load_state_dict(sd)
     base = synth.cheap_wave_batch(8, 480000, seed=11)
-    batches = [(base[:4] * (1.0 - 0.1 * k)).contiguous().pin_memory() for k in range(4)] + [base[4:6].contiguous().pin_memory()]
-    st = pipeline.StreamingTranscriber(m, 4, 480000, 0.5)
-    got = [(r.clone(), n.copy()) for r, n in st.run(batches)]
+    batches = [(base[:4] * (1.0 - 0.1 * k)).contiguous() for k in range(4)] + [base[4:6].contiguous()]
+    if input_format == "pcm16":
+        pcm = [torch.clamp(torch.round(b * 32768.0), -32768, 32767).to(torch.int16).pin_memory() for b in batches]
+        batches = [p.float() / 32768.0 for p in pcm]          # what a host-side decode of the same file gives
+        feed = pcm
+    else:
+        feed = [b.pin_memory() for b in batches]
+    st = pipeline.StreamingTranscriber(m, 4, 480000, 0.5, input_format=input_format, roll_format=roll_format)
+    got = [(r.clone(), n.copy()) for r, n in st.run(feed)]
     assert len(got) == 5
     for hb, (roll, notes) in zip(batches, got):
         want_notes, probs = pipeline.transcribe_chunks(m, hb.to(DEV), threshold=0.5, batch=4, return_probs=True)
         assert np.array_equal(notes, want_notes)
-        assert torch.equal(roll, (probs > 0.5).float().cpu())
+        want_roll = (probs > 0.5).float().cpu()
+        if roll_format == "bits":
+            assert roll.dtype == torch.int32 and roll.shape == (hb.shape[0], 88, (st.T + 31) // 32)
+            assert np.array_equal(pipeline.unpack_roll(roll, st.T), want_roll.numpy())
+        else:
+            assert torch.equal(roll, want_roll)
+    # copy=True hands out private copies: collecting the generator must not alias the two pinned slots
+    st2 = pipeline.StreamingTranscriber(m, 4, 480000, 0.5, input_format=input_format, roll_format=roll_format, copy=True)
+    kept = list(st2.run(feed))
+    for (r0, n0), (r1, n1) in zip(got, kept):
+        assert torch.equal(r0, r1) and np.array_equal(n0, n1)

@@ -41,6 +41,26 @@ def test_model_oracle_matches_reference_outputs(path):
     assert (pred.numpy() != g["pred"]).mean() < 1e-3
 
 
+@pytest.mark.parametrize("name", ["large", "small"])
+def test_model_oracle_matches_reference_at_canonical_shapes(name):
+    """tests/golden/canon_*.npz = the real reference modules at n_mels 320 / hidden 512 / 3 layers / T 938 on chord
+    log-mel (oracle/make_golden.py canonical): the port must reproduce them to fp32 rounding."""
+    g = np.load(os.path.join(GOLDEN, f"canon_{name}.npz"))
+    n_mels, H, L, B, T, seed = [int(v) for v in g["cfg"]]
+    mt = str(g["model_type"])
+    sd = synth.synth_state_dict(mt, n_mels, H, L, seed=seed, gain=float(g["gain"]))
+    x = torch.from_numpy(g["x"].astype(np.float32))
+    assert x.shape == (B, 1, n_mels, T)
+    # the stored input IS the oracle frontend's log-mel of the chord chunks, on the float16 grid
+    want = ofe.logmel(synth.piano_chord(int(g["chunks"][0]))).astype(np.float16).astype(np.float32)
+    assert np.abs(want - g["x"][0, 0].astype(np.float32)).max() <= 0.0625      # one fp16 ulp at |x| < 64 (libm differences)
+    torch.set_num_threads(os.cpu_count() or 4)
+    out = omodel.forward(sd, x, mt, H, L, return_all_heads=True)
+    out = out if isinstance(out, dict) else {"frame": out}
+    for k, v in out.items():
+        np.testing.assert_allclose(v.numpy(), g[k], atol=5e-5, rtol=0)
+
+
 def test_reference_rejects_zero_length_input():
     g = np.load(os.path.join(GOLDEN, "model_T0.npz"))
     assert "Kernel size" in str(g["raised"])      # the T==0 guard of the reference is unreachable
