@@ -72,6 +72,12 @@ int amt_logmel_f32(amt_frontend* fe, const float* wav, int B, int n_samples, int
  * (reference models/transcription_model.py:91-108, models/cnn_rnn_model.py:57-74
  * and :262-349), eval mode. */
 enum amt_model_kind { AMT_MODEL_CNN_RNN = 0, AMT_MODEL_CNN_RNN_LARGE = 1 };
+/* Arithmetic of the tensor-core contractions (the reference is fp32 throughout, models/cnn_rnn_model.py:69-70,309-311):
+ *   FAST    bf16 operands, fp32 accumulation: probabilities within 2e-3 of the fp32 reference at the canonical config;
+ *   PRECISE split-bf16 operands x = hi + lo (16 mantissa bits), three products hi*hi + lo*hi + hi*lo per contraction
+ *           (the K axis of every conv / linear tripled), fp32 accumulation: within 3e-4, at about a third of the speed.
+ * Packed-weight layouts differ between the two. */
+enum amt_precision { AMT_PRECISION_FAST = 0, AMT_PRECISION_PRECISE = 1 };
 
 typedef struct amt_model_config {
   int kind;             /* amt_model_kind */
@@ -81,6 +87,7 @@ typedef struct amt_model_config {
   int heads;            /* attention heads (8 in the reference) */
   int use_attention;    /* large only */
   int use_onset_offset; /* large only: shared_fc + frame/onset/offset heads */
+  int precision;        /* amt_precision */
 } amt_model_config;
 
 typedef struct amt_model amt_model;
@@ -93,6 +100,12 @@ int amt_model_set_tensor(amt_model* m, const char* name, const void* dev_ptr, si
 /* Verifies every tensor the configuration needs is present with the right size. */
 int amt_model_finalize(amt_model* m);
 size_t amt_model_workspace_bytes(const amt_model* m, int B, int T);
+/* Where an intermediate tensor of amt_model_forward(m, ., B, T, ...) lives inside the caller's workspace: byte offset
+ * and extent of buffer `name` ("act1", "feat", "gx", "seq_a", "seq_b", "rnn_f32", "qkv", "att", "proj", "normed",
+ * "shared", "logits", ... -- DESIGN.md section 3).  The workspace is the caller's memory, so after a forward the
+ * tensors can be read back from it: this is how the parity tests attribute an output difference to a stage
+ * (reference internals: models/cnn_rnn_model.py:262-349).  AMT_ERR_ARG for a buffer the configuration lacks. */
+int amt_model_workspace_layout(const amt_model* m, int B, int T, const char* name, size_t* offset, size_t* nbytes);
 /* logmel [B][1][n_mels][T] f32 -> frame/onset/offset logits [B][88][T] f32.
  * onset/offset may be NULL.  workspace: device scratch of at least
  * amt_model_workspace_bytes(m,B,T) bytes, 1024-byte aligned. */
@@ -183,10 +196,14 @@ int amt_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int 
  * Y[B][T][F or F/2][Cout] = act(conv_{kf x kt}(X) (+ 1x1 conv of X2 [B][T][F][Cin2]) + bias), optional
  * 2:1 max-pool over F.  W [Cout][kf*kt*Cin (+Cin2)] bf16 with K index (kf, kt, cin).
  * Built filters: 3x3 and 7x3 (kf x kt); Cout in {64, 128, 256}; Cin2 in {0, 32, 64k} and <= the
- * main channel block. */
+ * main channel block.  pool: bit 0 = 2:1 max-pool over F; bit 1 = split-bf16 output, Y [..][3*Cout] =
+ * [hi | lo | hi] per pixel (precise mode). */
 int amt_conv_bf16(const void* X, const void* X2, const void* W, const float* bias, void* Y, int B, int T,
                   int F, int Cin, int Cin2, int Cout, int kf, int kt, int relu, int pool,
                   amt_stream_t stream);
+/* Precise-mode operand split: x [rows][K] (f32 when in_f32, else bf16) -> out bf16 [rows][3K] =
+ * [hi(K) | lo(K) | hi(K)], hi = bf16(x), lo = bf16(x - hi) (0 for bf16 input).  K % 8 == 0. */
+int amt_split3_bf16(const void* x, int in_f32, void* out, int64_t rows, int K, amt_stream_t stream);
 /* LSTM recurrence (nn.LSTM eval forward, gate order i,f,g,o; reference models/cnn_rnn_model.py:45-52,
  * :212-228) over precomputed input projections gx = x W_ih^T + b_ih + b_hh, for n_seq independent
  * sequences (directions / stacked LSTMs) at once; see DESIGN.md section 4. */

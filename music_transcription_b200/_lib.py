@@ -23,7 +23,7 @@ class AmtError(RuntimeError):
 
 class ModelConfig(C.Structure):
     _fields_ = [("kind", C.c_int), ("n_mels", C.c_int), ("hidden", C.c_int), ("layers", C.c_int),
-                ("heads", C.c_int), ("use_attention", C.c_int), ("use_onset_offset", C.c_int)]
+                ("heads", C.c_int), ("use_attention", C.c_int), ("use_onset_offset", C.c_int), ("precision", C.c_int)]
 
 
 class LstmSeq(C.Structure):
@@ -53,6 +53,7 @@ _SIGS = {
     "amt_model_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
     "amt_model_finalize": (C.c_int, [C.c_void_p]),
     "amt_model_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "amt_model_workspace_layout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "amt_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "amt_sigmoid_threshold": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -68,6 +69,7 @@ _SIGS = {
                                 C.c_int, C.c_int, C.c_void_p]),
     "amt_conv_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "amt_split3_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "amt_lstm_scratch_bytes": (C.c_size_t, [C.POINTER(LstmSeq), C.c_int, C.c_int]),
     "amt_lstm_recurrence": (C.c_int, [C.POINTER(LstmSeq), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "amt_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),

@@ -304,6 +304,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int head = m % p.heads;
       const int b = m / p.heads;
       float lsum = 0.0f;
+      // This group takes the key blocks j with (j & 1) == jpar in THIS tile (the S / P buffer index runs over a global
+      // block counter, so with an odd number of blocks per tile the groups swap roles from tile to tile).  The partial
+      // row sums are filed by block parity, not by group, so the final sum always adds the same four partials in the same
+      // order: a tile's output does not depend on how many tiles its CTA processed before it (batch invariance).
+      const uint32_t jpar = grp ^ (g & 1u);
       ATT_TR(8);
       for (int j = 0; j < p.nb; ++j, ++g) {
         const uint32_t s = g & 1, ph = (g >> 1) & 1;
@@ -363,7 +368,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         copy_q(tl + 1);
       }
       // ---- tile epilogue: O / rowsum -> bf16 -> smem -> TMA store ----
-      lsum_x[part * kAttQ + row] = lsum;
+      lsum_x[(jpar * 2 + half) * kAttQ + row] = lsum;
       ptx::mbar_wait(o_full, tl & 1);              // every MMA of the tile retired
       ATT_TR(6);
       ptx::tc_fence_after();

@@ -83,7 +83,10 @@ constexpr int kConvThreads = 352;
 constexpr int kEpiWarp0 = 3;        // first epilogue warp
 constexpr int kEpiThreads = 256;
 
-template <int KC, int BN, int KF>
+// SPLIT (precise mode): the epilogue writes every output value as a split-bf16 pair, hi = bf16(x) and
+// lo = bf16(x - hi), into a [hi(BN) | lo(BN) | hi(BN)] channel group of 3*BN channels per pixel -- the operand layout
+// whose weights are packed [Wh | Wh | Wl], so the next layer's MMAs compute hi*Wh + lo*Wh + hi*Wl.
+template <int KC, int BN, int KF, bool SPLIT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -400,7 +403,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
         const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 64 + half * 32);
-        uint32_t pk[16];
+        uint32_t pk[16], pl[SPLIT ? 16 : 1];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 bb = b4[j];
@@ -417,23 +420,50 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           pk[2 * j] = ptx::pack_bf16(x0, x1);
           pk[2 * j + 1] = ptx::pack_bf16(x2, x3);
-        }
-        uint8_t* obuf = o_smem + (chunk_no & 1) * (128 * 128);
-        if (writer) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t c16 = static_cast<uint32_t>(half * 4 + j);
-            *reinterpret_cast<uint4*>(obuf + o_row + ((c16 ^ (ro & 7)) << 4)) =
-                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          if constexpr (SPLIT) {
+            pl[2 * j] = ptx::pack_bf16(x0 - __uint_as_float(pk[2 * j] << 16), x1 - __uint_as_float(pk[2 * j] & 0xffff0000u));
+            pl[2 * j + 1] = ptx::pack_bf16(x2 - __uint_as_float(pk[2 * j + 1] << 16), x3 - __uint_as_float(pk[2 * j + 1] & 0xffff0000u));
           }
         }
-        ptx::fence_proxy_async_smem();
-        // the buffer written NEXT (other parity) was last read by the store issued one chunk ago
-        if (issuer) ptx::bulk_wait_group_read0();
-        ptx::named_bar_sync(1, kEpiThreads);
-        if (issuer) {
-          ptx::tma_store_4d(&tmOut, obuf, c * 64, p.pool ? (f0 >> 1) : f0, t0, b);
-          ptx::bulk_commit_group();
+        if constexpr (SPLIT) {
+          // both staging buffers are used per chunk (hi, lo): wait until the previous chunk's stores have read them
+          if (issuer) ptx::bulk_wait_group_read0();
+          ptx::named_bar_sync(1, kEpiThreads);
+          if (writer) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t off = o_row + ((static_cast<uint32_t>(half * 4 + j) ^ (ro & 7)) << 4);
+              *reinterpret_cast<uint4*>(o_smem + off) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              *reinterpret_cast<uint4*>(o_smem + 128 * 128 + off) = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(1, kEpiThreads);
+          if (issuer) {
+            const int fo = p.pool ? (f0 >> 1) : f0;
+            ptx::tma_store_4d(&tmOut, o_smem, c * 64, fo, t0, b);
+            ptx::tma_store_4d(&tmOut, o_smem + 128 * 128, BN + c * 64, fo, t0, b);
+            ptx::tma_store_4d(&tmOut, o_smem, 2 * BN + c * 64, fo, t0, b);
+            ptx::bulk_commit_group();
+          }
+        } else {
+          uint8_t* obuf = o_smem + (chunk_no & 1) * (128 * 128);
+          if (writer) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t c16 = static_cast<uint32_t>(half * 4 + j);
+              *reinterpret_cast<uint4*>(obuf + o_row + ((c16 ^ (ro & 7)) << 4)) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          // the buffer written NEXT (other parity) was last read by the store issued one chunk ago
+          if (issuer) ptx::bulk_wait_group_read0();
+          ptx::named_bar_sync(1, kEpiThreads);
+          if (issuer) {
+            ptx::tma_store_4d(&tmOut, obuf, c * 64, p.pool ? (f0 >> 1) : f0, t0, b);
+            ptx::bulk_commit_group();
+          }
         }
       }
     }
@@ -450,11 +480,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 }
 
-template <int KC, int BN, int KF>
+template <int KC, int BN, int KF, bool SPLIT>
 static int launch_conv_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
                             const CUtensorMap& o, const ConvHaloParams& p, cudaStream_t stream) {
   using Cfg = ConvHaloCfg<KC, BN>;
-  AMT_FUNC_ATTR((conv_halo_kernel<KC, BN, KF>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  AMT_FUNC_ATTR((conv_halo_kernel<KC, BN, KF, SPLIT>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   ConvHaloParams q = p;
   q.resident = (p.cblks * KF * 3 + p.cblks2 <= Cfg::kBStages) ? 1 : 0;
   if constexpr (Cfg::kPair) {
@@ -472,11 +502,11 @@ static int launch_conv_halo(const CUtensorMap& a0, const CUtensorMap& a1, const 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AMT_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<KC, BN, KF>, a0, a1, b0, b1, o, q));
+    AMT_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<KC, BN, KF, SPLIT>, a0, a1, b0, b1, o, q));
     count_launch();
   } else {
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    conv_halo_kernel<KC, BN, KF><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, o, q);
+    conv_halo_kernel<KC, BN, KF, SPLIT><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, o, q);
     AMT_CHECK_LAUNCH();
   }
   return 0;
@@ -485,7 +515,7 @@ static int launch_conv_halo(const CUtensorMap& a0, const CUtensorMap& a1, const 
 static CUtensorMapSwizzle swizzle_for(int kc) { return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B; }
 
 int run_conv_halo(const void* X, int C, const void* X2, int C2, int B, int T, int F, const void* W, const float* bias,
-                  int N, int kf, int kt, void* out, int relu, int pool, cudaStream_t stream) {
+                  int N, int kf, int kt, void* out, int relu, int pool, int split, cudaStream_t stream) {
   AMT_TRY(ensure_device());
   AMT_REQUIRE(B > 0 && T > 0 && F > 0, "conv: empty problem");
   AMT_REQUIRE(C == 32 || C % 64 == 0, "conv: Cin (%d) must be 32 or a multiple of 64", C);
@@ -503,8 +533,9 @@ int run_conv_halo(const void* X, int C, const void* X2, int C2, int B, int T, in
   {
     const int Fout = pool ? F / 2 : F;
     AMT_REQUIRE(Fout >= 1, "conv: pooled output is empty");
-    uint64_t dims[4] = {(uint64_t)N, (uint64_t)Fout, (uint64_t)T, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)N * 2, (uint64_t)Fout * N * 2, (uint64_t)T * Fout * N * 2};
+    const uint64_t No = split ? 3ull * N : N;          // split: [hi(N) | lo(N) | hi(N)] per pixel
+    uint64_t dims[4] = {No, (uint64_t)Fout, (uint64_t)T, (uint64_t)B};
+    uint64_t str[3] = {No * 2, (uint64_t)Fout * No * 2, (uint64_t)T * Fout * No * 2};
     uint32_t box[4] = {64, (uint32_t)(pool ? kTileF / 2 : kTileF), kTileT, 1};
     AMT_TRY(encode_tmap_bf16(&om, out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
@@ -553,19 +584,23 @@ int run_conv_halo(const void* X, int C, const void* X2, int C2, int B, int T, in
   p.relu = relu;
   p.resident = 0;
 
+#define AMT_CONV_DISPATCH(KC_, N_, KF_)                                                                   \
+  return split ? launch_conv_halo<KC_, N_, KF_, true>(a0, a1, b0, b1, om, p, stream)                    \
+               : launch_conv_halo<KC_, N_, KF_, false>(a0, a1, b0, b1, om, p, stream)
   if (kf == 7) {
-    if (N == 64) return launch_conv_halo<64, 64, 7>(a0, a1, b0, b1, om, p, stream);
-    if (N == 128) return launch_conv_halo<64, 128, 7>(a0, a1, b0, b1, om, p, stream);
-    return launch_conv_halo<64, 256, 7>(a0, a1, b0, b1, om, p, stream);
+    if (N == 64) AMT_CONV_DISPATCH(64, 64, 7);
+    if (N == 128) AMT_CONV_DISPATCH(64, 128, 7);
+    AMT_CONV_DISPATCH(64, 256, 7);
   }
   if (KC == 32) {
-    if (N == 64) return launch_conv_halo<32, 64, 3>(a0, a1, b0, b1, om, p, stream);
-    if (N == 128) return launch_conv_halo<32, 128, 3>(a0, a1, b0, b1, om, p, stream);
-    return launch_conv_halo<32, 256, 3>(a0, a1, b0, b1, om, p, stream);
+    if (N == 64) AMT_CONV_DISPATCH(32, 64, 3);
+    if (N == 128) AMT_CONV_DISPATCH(32, 128, 3);
+    AMT_CONV_DISPATCH(32, 256, 3);
   }
-  if (N == 64) return launch_conv_halo<64, 64, 3>(a0, a1, b0, b1, om, p, stream);
-  if (N == 128) return launch_conv_halo<64, 128, 3>(a0, a1, b0, b1, om, p, stream);
-  return launch_conv_halo<64, 256, 3>(a0, a1, b0, b1, om, p, stream);
+  if (N == 64) AMT_CONV_DISPATCH(64, 64, 3);
+  if (N == 128) AMT_CONV_DISPATCH(64, 128, 3);
+  AMT_CONV_DISPATCH(64, 256, 3);
+#undef AMT_CONV_DISPATCH
 }
 
 }  // namespace amt

@@ -6,17 +6,20 @@ namespace amt {
 
 // halo-tile implicit-GEMM convolution (conv_halo.cu): X [B][T][F][C], optional 1x1 skip source X2 [B][T][F][C2],
 // W [N][kf*kt*C + C2] (K index = (kf, kt, c)), out [B][T][F or F/2][N] bf16
+// split != 0: out [B][T][F'][3N] = [hi(N) | lo(N) | hi(N)] per pixel
 int run_conv_halo(const void* X, int C, const void* X2, int C2, int B, int T, int F, const void* W, const float* bias,
-                  int N, int kf, int kt, void* out, int relu, int pool, cudaStream_t stream);
+                  int N, int kf, int kt, void* out, int relu, int pool, int split, cudaStream_t stream);
 int run_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, long long ldc, int relu,
              int out_f32, cudaStream_t stream);
 int run_lstm(const amt_lstm_seq* seqs, int n_seq, int B, int T, void* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t lstm_scratch_bytes(const amt_lstm_seq* seqs, int n_seq, int B);
 int run_attention(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip, cudaStream_t stream);
 int run_attention_tc(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip, cudaStream_t stream);
-int run_conv1(const float* x, const float* w, const float* bias, void* out, int B, int Fin, int T, cudaStream_t stream);
+// split != 0 (precise mode): outputs in the split-bf16 layout [hi | lo | hi (| 0)] per channel group
+int run_conv1(const float* x, const float* w, const float* bias, void* out, int B, int Fin, int T, int split, cudaStream_t stream);
 int run_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, void* out, long long rows,
-                      int D, float eps, cudaStream_t stream);
+                      int D, float eps, int split, cudaStream_t stream);
+int run_split3(const void* x, int in_f32, void* out, long long rows, int K, cudaStream_t stream);
 int run_heads_transpose(const float* in, int ld, int B, int T, int n_heads, float* o0, float* o1, float* o2,
                         cudaStream_t stream);
 

@@ -74,6 +74,9 @@ struct amt_model {
   int H, Hl, D;         // hidden, local hidden, rnn output width
   int Ng0;              // gate columns of layer 0 (all sequences)
   int n_out, n_out_pad; // head columns (88 * n_heads) and padded GEMM N
+  // precise mode (cfg.precision == 1): split-bf16 operands, K axis of every contraction tripled
+  int KM;               // K multiplier: 1 (fast) or 3 (precise: [hi | lo | hi] x [Wh | Wh | Wl])
+  int C1;               // channels of one stem-output pixel: 32, or the 128-channel group [hi | lo | hi | 0]
 };
 
 namespace amt {
@@ -85,26 +88,27 @@ static std::vector<Expect> expected_tensors(const amt_model& m) {
   std::vector<Expect> e;
   auto bf = [](size_t n) { return n * 2; };
   auto f32 = [](size_t n) { return n * 4; };
+  const size_t km = m.KM, c1 = m.C1;       // operand channels: c1 for the stem output, km * C elsewhere
   e.push_back({"conv1.w", f32(32 * 9)});
   e.push_back({"conv1.b", f32(32)});
   if (c.kind == AMT_MODEL_CNN_RNN) {
-    e.push_back({"c2.w", bf(64ull * 9 * 32)});
+    e.push_back({"c2.w", bf(64ull * 9 * c1)});
     e.push_back({"c2.b", f32(64)});
   } else {
-    e.push_back({"res1.c1.w", bf(64ull * 9 * 32)});
+    e.push_back({"res1.c1.w", bf(64ull * 9 * c1)});
     e.push_back({"res1.c1.b", f32(64)});
-    e.push_back({"res1.c2.w", bf(64ull * (9 * 64 + 32))});
+    e.push_back({"res1.c2.w", bf(64ull * (9 * 64 * km + c1))});
     e.push_back({"res1.c2.b", f32(64)});
-    e.push_back({"res2.c1.w", bf(128ull * 9 * 64)});
+    e.push_back({"res2.c1.w", bf(128ull * 9 * 64 * km)});
     e.push_back({"res2.c1.b", f32(128)});
-    e.push_back({"res2.c2.w", bf(128ull * (9 * 128 + 64))});
+    e.push_back({"res2.c2.w", bf(128ull * (9 * 128 + 64) * km)});
     e.push_back({"res2.c2.b", f32(128)});
-    e.push_back({"freq.w", bf(256ull * 21 * 128)});
+    e.push_back({"freq.w", bf(256ull * 21 * 128 * km)});
     e.push_back({"freq.b", f32(256)});
   }
   for (int l = 0; l < c.layers; ++l) {
     const size_t N = l == 0 ? m.Ng0 : 8ull * m.H;
-    const size_t K = l == 0 ? m.Kfeat : 2ull * m.H;
+    const size_t K = km * (l == 0 ? m.Kfeat : 2ull * m.H);
     e.push_back({"rnn" + std::to_string(l) + ".wih", bf(N * K)});
     e.push_back({"rnn" + std::to_string(l) + ".b", f32(N)});
     for (int d = 0; d < 2; ++d) e.push_back({"rnn" + std::to_string(l) + ".whh" + std::to_string(d), bf(4ull * m.H * m.H)});
@@ -112,22 +116,22 @@ static std::vector<Expect> expected_tensors(const amt_model& m) {
   if (c.kind == AMT_MODEL_CNN_RNN_LARGE) {
     for (int d = 0; d < 2; ++d) e.push_back({"loc.whh" + std::to_string(d), bf(4ull * m.Hl * m.Hl)});
     if (c.use_attention) {
-      e.push_back({"attn.qkv.w", bf(3ull * m.D * m.D)});
+      e.push_back({"attn.qkv.w", bf(3ull * m.D * m.D * km)});
       e.push_back({"attn.qkv.b", f32(3ull * m.D)});
-      e.push_back({"attn.proj.w", bf(1ull * m.D * m.D)});
+      e.push_back({"attn.proj.w", bf(1ull * m.D * m.D * km)});
       e.push_back({"attn.proj.b", f32(m.D)});
       e.push_back({"ln.w", f32(m.D)});
       e.push_back({"ln.b", f32(m.D)});
     }
     if (c.use_onset_offset) {
-      e.push_back({"fc1.w", bf(1ull * m.H * m.D)});
+      e.push_back({"fc1.w", bf(1ull * m.H * m.D * km)});
       e.push_back({"fc1.b", f32(m.H)});
-      e.push_back({"heads.w", bf(1ull * m.n_out_pad * m.H)});
+      e.push_back({"heads.w", bf(1ull * m.n_out_pad * m.H * km)});
     } else {
-      e.push_back({"heads.w", bf(1ull * m.n_out_pad * m.D)});
+      e.push_back({"heads.w", bf(1ull * m.n_out_pad * m.D * km)});
     }
   } else {
-    e.push_back({"heads.w", bf(1ull * m.n_out_pad * m.D)});
+    e.push_back({"heads.w", bf(1ull * m.n_out_pad * m.D * km)});
   }
   e.push_back({"heads.b", f32(m.n_out_pad)});
   return e;
@@ -152,40 +156,47 @@ struct Buffers {
   void* rnn_bf16; float* rnn_f32;                // final LSTM features
   void *qkv, *att; float* proj; void* normed; void* shared; float* logits;
   void* lstm_scratch; size_t lstm_scratch_bytes;
+  // precise mode only: fp32 outputs of the stages whose consumers need split operands
+  float* seq_f32; float* shared_f32; void* att_split;
 };
 
 static size_t carve(const amt_model& m, int B, int T, void* ws, Buffers* b) {
   Workspace w(ws);
   const size_t BT = static_cast<size_t>(B) * T;
   const bool large = m.cfg.kind == AMT_MODEL_CNN_RNN_LARGE;
-  b->act1 = w.take(BT * m.F1 * 32 * 2);
+  const size_t km = m.KM;                   // bf16 operand tensors are km x wider in precise mode
+  const bool precise = km > 1;
+  b->act1 = w.take(BT * m.F1 * m.C1 * 2);
   if (large) {
-    b->h1 = w.take(BT * m.F1 * 64 * 2);
-    b->act2 = w.take(BT * m.F2 * 64 * 2);
-    b->h2 = w.take(BT * m.F2 * 128 * 2);
-    b->act3 = w.take(BT * m.F2 * 128 * 2);
-    b->feat = w.take(BT * m.F3 * 256 * 2);
+    b->h1 = w.take(BT * m.F1 * 64 * km * 2);
+    b->act2 = w.take(BT * m.F2 * 64 * km * 2);
+    b->h2 = w.take(BT * m.F2 * 128 * km * 2);
+    b->act3 = w.take(BT * m.F2 * 128 * km * 2);
+    b->feat = w.take(BT * m.F3 * 256 * km * 2);
   } else {
     b->h1 = b->act2 = b->h2 = b->act3 = nullptr;
-    b->feat = w.take(BT * m.F2 * 64 * 2);
+    b->feat = w.take(BT * m.F2 * 64 * km * 2);
   }
   const size_t gcols = std::max<size_t>(m.Ng0, 8ull * m.H);
   b->gx = static_cast<float*>(w.take(BT * gcols * 4));
-  b->seq_a = w.take(BT * 2 * m.H * 2);
-  b->seq_b = w.take(BT * 2 * m.H * 2);
-  b->rnn_bf16 = w.take(BT * m.D * 2);
+  b->seq_a = w.take(BT * 2 * m.H * km * 2);
+  b->seq_b = w.take(BT * 2 * m.H * km * 2);
+  b->rnn_bf16 = w.take(BT * m.D * km * 2);
   b->rnn_f32 = static_cast<float*>(w.take(BT * m.D * 4));
   if (large && m.cfg.use_attention) {
     b->qkv = w.take(BT * 3 * m.D * 2);
     b->att = w.take(BT * m.D * 2);
     b->proj = static_cast<float*>(w.take(BT * m.D * 4));
-    b->normed = w.take(BT * m.D * 2);
+    b->normed = w.take(BT * m.D * km * 2);
   } else {
     b->qkv = b->att = b->normed = nullptr;
     b->proj = nullptr;
   }
-  b->shared = (large && m.cfg.use_onset_offset) ? w.take(BT * m.H * 2) : nullptr;
+  b->shared = (large && m.cfg.use_onset_offset) ? w.take(BT * m.H * km * 2) : nullptr;
   b->logits = static_cast<float*>(w.take(BT * m.n_out_pad * 4));
+  b->seq_f32 = precise ? static_cast<float*>(w.take(BT * 2 * m.H * 4)) : nullptr;
+  b->shared_f32 = (precise && large && m.cfg.use_onset_offset) ? static_cast<float*>(w.take(BT * m.H * 4)) : nullptr;
+  b->att_split = (precise && large && m.cfg.use_attention) ? w.take(BT * m.D * km * 2) : nullptr;
   // recurrence scratch: worst case is layer 0 of the large model (4 sequences)
   amt_lstm_seq seqs[4];
   int n = 0;
@@ -199,15 +210,17 @@ static size_t carve(const amt_model& m, int B, int T, void* ws, Buffers* b) {
 static const void* T_(const amt_model& m, const std::string& n) { return m.tensors.at(n).ptr; }
 static const float* F_(const amt_model& m, const std::string& n) { return static_cast<const float*>(m.tensors.at(n).ptr); }
 
-static int conv(const amt_model&, const void* X, int C, const void* X2, int C2, int B, int T, int F, const void* W,
+static int conv(const amt_model& m, const void* X, int C, const void* X2, int C2, int B, int T, int F, const void* W,
                 const float* bias, int N, int kf, int kt, void* out, int pool, cudaStream_t s) {
-  return run_conv_halo(X, C, X2, C2, B, T, F, W, bias, N, kf, kt, out, 1, pool, s);
+  return run_conv_halo(X, C, X2, C2, B, T, F, W, bias, N, kf, kt, out, 1, pool, m.KM > 1, s);
 }
 
 static int forward(amt_model& m, const float* logmel, int B, int T, float* frame, float* onset, float* offset,
                    void* ws, cudaStream_t s) {
   const amt_model_config& c = m.cfg;
   const bool large = c.kind == AMT_MODEL_CNN_RNN_LARGE;
+  const bool precise = m.KM > 1;
+  const int km = m.KM;
   Buffers b;
   carve(m, B, T, ws, &b);
   const int BT = B * T;
@@ -220,21 +233,22 @@ static int forward(amt_model& m, const float* logmel, int B, int T, float* frame
     if (_st != 0) return _st;           \
   } while (0)
 
-  // ---- CNN ----
-  STAGE("conv1", run_conv1(logmel, F_(m, "conv1.w"), F_(m, "conv1.b"), b.act1, B, c.n_mels, T, s));
+  // ---- CNN ----  (precise: every activation tensor carries km = 3 x the channels, [hi | lo | hi] per pixel)
+  STAGE("conv1", run_conv1(logmel, F_(m, "conv1.w"), F_(m, "conv1.b"), b.act1, B, c.n_mels, T, precise, s));
   if (large) {
-    STAGE("res1.c1", conv(m, b.act1, 32, nullptr, 0, B, T, m.F1, T_(m, "res1.c1.w"), F_(m, "res1.c1.b"), 64, 3, 3, b.h1, 0, s));
-    STAGE("res1.c2", conv(m, b.h1, 64, b.act1, 32, B, T, m.F1, T_(m, "res1.c2.w"), F_(m, "res1.c2.b"), 64, 3, 3, b.act2, 1, s));
-    STAGE("res2.c1", conv(m, b.act2, 64, nullptr, 0, B, T, m.F2, T_(m, "res2.c1.w"), F_(m, "res2.c1.b"), 128, 3, 3, b.h2, 0, s));
-    STAGE("res2.c2", conv(m, b.h2, 128, b.act2, 64, B, T, m.F2, T_(m, "res2.c2.w"), F_(m, "res2.c2.b"), 128, 3, 3, b.act3, 0, s));
-    STAGE("freq", conv(m, b.act3, 128, nullptr, 0, B, T, m.F2, T_(m, "freq.w"), F_(m, "freq.b"), 256, 7, 3, b.feat, 1, s));
+    STAGE("res1.c1", conv(m, b.act1, m.C1, nullptr, 0, B, T, m.F1, T_(m, "res1.c1.w"), F_(m, "res1.c1.b"), 64, 3, 3, b.h1, 0, s));
+    STAGE("res1.c2", conv(m, b.h1, 64 * km, b.act1, m.C1, B, T, m.F1, T_(m, "res1.c2.w"), F_(m, "res1.c2.b"), 64, 3, 3, b.act2, 1, s));
+    STAGE("res2.c1", conv(m, b.act2, 64 * km, nullptr, 0, B, T, m.F2, T_(m, "res2.c1.w"), F_(m, "res2.c1.b"), 128, 3, 3, b.h2, 0, s));
+    STAGE("res2.c2", conv(m, b.h2, 128 * km, b.act2, 64 * km, B, T, m.F2, T_(m, "res2.c2.w"), F_(m, "res2.c2.b"), 128, 3, 3, b.act3, 0, s));
+    STAGE("freq", conv(m, b.act3, 128 * km, nullptr, 0, B, T, m.F2, T_(m, "freq.w"), F_(m, "freq.b"), 256, 7, 3, b.feat, 1, s));
   } else {
-    STAGE("c2", conv(m, b.act1, 32, nullptr, 0, B, T, m.F1, T_(m, "c2.w"), F_(m, "c2.b"), 64, 3, 3, b.feat, 1, s));
+    STAGE("c2", conv(m, b.act1, m.C1, nullptr, 0, B, T, m.F1, T_(m, "c2.w"), F_(m, "c2.b"), 64, 3, 3, b.feat, 1, s));
   }
 
   // ---- BiLSTM stack (+ the parallel local BiLSTM of the large model on layer 0) ----
+  // precise: the recurrences write fp32 outputs, which split3 turns into the next GEMM's [hi | lo | hi] operand
   const void* x = b.feat;
-  int K = m.Kfeat;
+  int K = m.Kfeat * km;
   for (int l = 0; l < c.layers; ++l) {
     const std::string pre = "rnn" + std::to_string(l);
     const int N = l == 0 ? m.Ng0 : 8 * m.H;
@@ -248,43 +262,55 @@ static int forward(amt_model& m, const float* logmel, int B, int T, float* frame
       amt_lstm_seq& q = seqs[n++];
       q.whh = T_(m, pre + ".whh" + std::to_string(d));
       q.gx = b.gx + d * 4 * m.H;
-      q.out_bf16 = static_cast<__nv_bfloat16*>(out_bf) + d * m.H;
-      q.out_f32 = last ? b.rnn_f32 + d * m.H : nullptr;
-      q.H = m.H; q.reverse = d; q.ld_gx = N; q.ld_out = ld_out; q.ld_out32 = m.D;
+      q.out_bf16 = precise ? nullptr : static_cast<__nv_bfloat16*>(out_bf) + d * m.H;
+      q.out_f32 = last ? b.rnn_f32 + d * m.H : (precise ? b.seq_f32 + d * m.H : nullptr);
+      q.H = m.H; q.reverse = d; q.ld_gx = N; q.ld_out = ld_out; q.ld_out32 = last ? m.D : 2 * m.H;
     }
     if (large && l == 0) {
       for (int d = 0; d < 2; ++d) {
         amt_lstm_seq& q = seqs[n++];
         q.whh = T_(m, "loc.whh" + std::to_string(d));
         q.gx = b.gx + 8 * m.H + d * 4 * m.Hl;
-        q.out_bf16 = static_cast<__nv_bfloat16*>(b.rnn_bf16) + 2 * m.H + d * m.Hl;
+        q.out_bf16 = precise ? nullptr : static_cast<__nv_bfloat16*>(b.rnn_bf16) + 2 * m.H + d * m.Hl;
         q.out_f32 = b.rnn_f32 + 2 * m.H + d * m.Hl;
         q.H = m.Hl; q.reverse = d; q.ld_gx = N; q.ld_out = m.D; q.ld_out32 = m.D;
       }
     }
     STAGE(pre + ".rec", run_lstm(seqs, n, B, T, b.lstm_scratch, b.lstm_scratch_bytes, s));
+    if (precise && !last) STAGE(pre + ".split", run_split3(b.seq_f32, 1, out_bf, BT, 2 * m.H, s));
     x = out_bf;
-    K = 2 * m.H;
+    K = 2 * m.H * km;
   }
+  if (precise) STAGE("rnn.split", run_split3(b.rnn_f32, 1, b.rnn_bf16, BT, m.D, s));
 
   // ---- attention + residual LayerNorm ----
   const void* head_in = b.rnn_bf16;
   if (large && c.use_attention) {
-    STAGE("attn.qkv", run_gemm(b.rnn_bf16, T_(m, "attn.qkv.w"), F_(m, "attn.qkv.b"), b.qkv, BT, 3 * m.D, m.D, 3 * m.D, 0, 0, s));
+    STAGE("attn.qkv", run_gemm(b.rnn_bf16, T_(m, "attn.qkv.w"), F_(m, "attn.qkv.b"), b.qkv, BT, 3 * m.D, m.D * km, 3 * m.D, 0, 0, s));
     STAGE("attn.core", run_attention(b.qkv, b.att, B, T, c.heads, m.D / c.heads, 10.0f, s));
-    STAGE("attn.proj", run_gemm(b.att, T_(m, "attn.proj.w"), F_(m, "attn.proj.b"), b.proj, BT, m.D, m.D, m.D, 0, 1, s));
-    STAGE("add_ln", run_add_layernorm(b.rnn_f32, b.proj, F_(m, "ln.w"), F_(m, "ln.b"), b.normed, BT, m.D, 1e-6f, s));
+    const void* att_in = b.att;
+    if (precise) {      // the attention core keeps bf16 q, k, v, P (< 1e-4 on the probabilities); its output has lo = 0
+      STAGE("attn.split", run_split3(b.att, 0, b.att_split, BT, m.D, s));
+      att_in = b.att_split;
+    }
+    STAGE("attn.proj", run_gemm(att_in, T_(m, "attn.proj.w"), F_(m, "attn.proj.b"), b.proj, BT, m.D, m.D * km, m.D, 0, 1, s));
+    STAGE("add_ln", run_add_layernorm(b.rnn_f32, b.proj, F_(m, "ln.w"), F_(m, "ln.b"), b.normed, BT, m.D, 1e-6f, precise, s));
     head_in = b.normed;
   }
 
   // ---- output heads ----
   int n_heads = 1;
   if (large && c.use_onset_offset) {
-    STAGE("fc1", run_gemm(head_in, T_(m, "fc1.w"), F_(m, "fc1.b"), b.shared, BT, m.H, m.D, m.H, 1, 0, s));
-    STAGE("heads", run_gemm(b.shared, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.H, m.n_out_pad, 0, 1, s));
+    if (precise) {
+      STAGE("fc1", run_gemm(head_in, T_(m, "fc1.w"), F_(m, "fc1.b"), b.shared_f32, BT, m.H, m.D * km, m.H, 1, 1, s));
+      STAGE("fc1.split", run_split3(b.shared_f32, 1, b.shared, BT, m.H, s));
+    } else {
+      STAGE("fc1", run_gemm(head_in, T_(m, "fc1.w"), F_(m, "fc1.b"), b.shared, BT, m.H, m.D, m.H, 1, 0, s));
+    }
+    STAGE("heads", run_gemm(b.shared, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.H * km, m.n_out_pad, 0, 1, s));
     n_heads = 3;
   } else {
-    STAGE("heads", run_gemm(head_in, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.D, m.n_out_pad, 0, 1, s));
+    STAGE("heads", run_gemm(head_in, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.D * km, m.n_out_pad, 0, 1, s));
   }
   STAGE("heads.transpose", run_heads_transpose(b.logits, m.n_out_pad, B, T, n_heads, frame, n_heads == 3 ? onset : nullptr,
                                                n_heads == 3 ? offset : nullptr, s));
@@ -310,8 +336,12 @@ int amt_model_create(const amt_model_config* cfg, amt_model** out) {
     const int hd = 3 * cfg->hidden / 8;
     AMT_REQUIRE(hd == 48 || hd == 96 || hd == 144 || hd == 192, "model_create: head_dim %d unsupported (hidden <= 512 with attention)", hd);
   }
+  AMT_REQUIRE(cfg->precision == AMT_PRECISION_FAST || cfg->precision == AMT_PRECISION_PRECISE,
+              "model_create: precision %d unknown (0 = fast bf16, 1 = precise split-bf16)", cfg->precision);
   auto* m = new amt_model();
   m->cfg = *cfg;
+  m->KM = cfg->precision == AMT_PRECISION_PRECISE ? 3 : 1;
+  m->C1 = cfg->precision == AMT_PRECISION_PRECISE ? 128 : 32;
   m->F1 = cfg->n_mels / 2;
   m->F2 = m->F1 / 2;
   m->F3 = m->F2 / 2;
@@ -389,6 +419,33 @@ int amt_model_profile_in_flight(amt_model* m, char* name, int cap) {
   }
   name[0] = 0;
   return -1;
+}
+
+int amt_model_workspace_layout(const amt_model* m, int B, int T, const char* name, size_t* offset, size_t* nbytes) {
+  using namespace amt;
+  AMT_REQUIRE(m && name && offset && nbytes && B >= 1 && T >= 1, "model_workspace_layout: bad arguments");
+  Buffers b;
+  uint8_t* const base = reinterpret_cast<uint8_t*>(uintptr_t(1) << 20);       // fake base: only differences are used
+  const size_t total = carve(*m, B, T, base, &b);
+  const struct { const char* n; const void* p; } tab[] = {
+      {"act1", b.act1}, {"h1", b.h1}, {"act2", b.act2}, {"h2", b.h2}, {"act3", b.act3}, {"feat", b.feat}, {"gx", b.gx},
+      {"seq_a", b.seq_a}, {"seq_b", b.seq_b}, {"rnn_bf16", b.rnn_bf16}, {"rnn_f32", b.rnn_f32}, {"qkv", b.qkv},
+      {"att", b.att}, {"proj", b.proj}, {"normed", b.normed}, {"shared", b.shared}, {"logits", b.logits},
+      {"lstm_scratch", b.lstm_scratch}};
+  std::vector<size_t> offs;
+  for (const auto& e : tab) if (e.p) offs.push_back(static_cast<const uint8_t*>(e.p) - base);
+  offs.push_back(total);
+  for (const auto& e : tab) {
+    if (strcmp(e.n, name) != 0) continue;
+    if (!e.p) return set_error(AMT_ERR_ARG, "model_workspace_layout: this configuration has no buffer '%s'", name);
+    const size_t off = static_cast<const uint8_t*>(e.p) - base;
+    size_t next = total;
+    for (size_t o : offs) if (o > off && o < next) next = o;
+    *offset = off;
+    *nbytes = next - off;                 // up to the next buffer (includes the 1 KB alignment padding)
+    return 0;
+  }
+  return set_error(AMT_ERR_ARG, "model_workspace_layout: unknown buffer '%s'", name);
 }
 
 size_t amt_model_workspace_bytes(const amt_model* m, int B, int T) {

@@ -20,9 +20,17 @@ namespace amt {
 constexpr int kC1T = 64, kC1F = 32;   // outputs per CTA: 64 frames x 32 pooled bins
 constexpr int kC1Rows = 2 * kC1F + 2, kC1Pitch = kC1T + 3;   // 66 input rows, odd pitch (conflict-free)
 
+// SPLIT (precise mode): the pixel's 32 channels are written as a 128-channel group [hi | lo | hi | 0] with
+// hi = bf16(x), lo = bf16(x - hi) -- the split-bf16 operand layout of DESIGN.md section 5.
+__device__ __forceinline__ uint32_t pack_bf16_lo(float x0, float x1, uint32_t hi) {
+  return ptx::pack_bf16(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
+}
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                     int Fin, int T, int Fout) {
+  constexpr int CS = SPLIT ? 128 : 32;             // channel stride of one output pixel
   __shared__ float tile[kC1Rows][kC1Pitch];
   const int tid = threadIdx.x;
   const int t0 = blockIdx.x * kC1T, fo0 = blockIdx.y * kC1F, b = blockIdx.z;
@@ -50,7 +58,7 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x,
     win[a][1] = tile[2 * fl + a][0];
     win[a][2] = tile[2 * fl + a][1];
   }
-  __nv_bfloat16* orow = out + ((static_cast<size_t>(b) * T + t0) * Fout + fo) * 32 + 4 * cg;
+  __nv_bfloat16* orow = out + ((static_cast<size_t>(b) * T + t0) * Fout + fo) * CS + 4 * cg;
   const int tmax = min(kC1T, T - t0);
   for (int tl = 0; tl < tmax; ++tl) {
 #pragma unroll
@@ -72,17 +80,66 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x,
         }
       r[c] = fmaxf(fmaxf(a0, a1), 0.0f);
     }
-    if (fo < Fout)
-      *reinterpret_cast<uint2*>(orow + static_cast<size_t>(tl) * Fout * 32) =
-          make_uint2(ptx::pack_bf16(r[0], r[1]), ptx::pack_bf16(r[2], r[3]));
+    if (fo < Fout) {
+      const uint32_t h0 = ptx::pack_bf16(r[0], r[1]), h1 = ptx::pack_bf16(r[2], r[3]);
+      uint2* o = reinterpret_cast<uint2*>(orow + static_cast<size_t>(tl) * Fout * CS);
+      o[0] = make_uint2(h0, h1);
+      if constexpr (SPLIT) {
+        o[8] = make_uint2(pack_bf16_lo(r[0], r[1], h0), pack_bf16_lo(r[2], r[3], h1));     // + 32 channels
+        o[16] = make_uint2(h0, h1);                                                         // + 64
+        o[24] = make_uint2(0u, 0u);                                                         // + 96: padding
+      }
+    }
   }
 }
 
-int run_conv1(const float* x, const float* w, const float* bias, void* out, int B, int Fin, int T, cudaStream_t stream) {
+int run_conv1(const float* x, const float* w, const float* bias, void* out, int B, int Fin, int T, int split,
+              cudaStream_t stream) {
   const int Fout = Fin / 2;
   AMT_REQUIRE(Fout >= 1 && T >= 1 && B >= 1 && B <= 65535, "conv1: bad sizes");
   dim3 grid(ceil_div(T, kC1T), ceil_div(Fout, kC1F), B);
-  conv1_kernel<<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout);
+  if (split) conv1_kernel<true><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout);
+  else conv1_kernel<false><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout);
+  AMT_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------
+// split3: x [rows][K] (f32, or bf16 whose lo part is then zero) -> bf16 [rows][3K] = [hi(K) | lo(K) | hi(K)]:
+// the A operand of a precise-mode GEMM (weights packed as [Wh | Wh | Wl]).  HBM-bound, 8 elements per thread.
+// ----------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256) split3_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows,
+                                                     int K) {
+  const int kv = K >> 3;
+  const long long total = rows * kv;
+  for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
+    const long long row = e / kv;
+    const int c = static_cast<int>(e - row * kv) << 3;
+    uint4 hi, lo;
+    if constexpr (sizeof(TIn) == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x + row * K + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(x + row * K + c) + 1);
+      hi = make_uint4(ptx::pack_bf16(a.x, a.y), ptx::pack_bf16(a.z, a.w), ptx::pack_bf16(b.x, b.y), ptx::pack_bf16(b.z, b.w));
+      lo = make_uint4(pack_bf16_lo(a.x, a.y, hi.x), pack_bf16_lo(a.z, a.w, hi.y), pack_bf16_lo(b.x, b.y, hi.z),
+                      pack_bf16_lo(b.z, b.w, hi.w));
+    } else {
+      hi = __ldg(reinterpret_cast<const uint4*>(x + row * K + c));
+      lo = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __nv_bfloat16* o = out + row * 3 * K + c;
+    *reinterpret_cast<uint4*>(o) = hi;
+    *reinterpret_cast<uint4*>(o + K) = lo;
+    *reinterpret_cast<uint4*>(o + 2 * K) = hi;
+  }
+}
+
+int run_split3(const void* x, int in_f32, void* out, long long rows, int K, cudaStream_t stream) {
+  AMT_REQUIRE(rows >= 1 && K >= 8 && K % 8 == 0, "split3: K (%d) must be a positive multiple of 8", K);
+  const long long total = rows * (K >> 3);
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((total + 255) / 256, 16ll * num_sms()));
+  if (in_f32) split3_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), rows, K);
+  else split3_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), rows, K);
   AMT_CHECK_LAUNCH();
   return 0;
 }
@@ -93,6 +150,7 @@ int run_conv1(const float* x, const float* w, const float* bias, void* out, int 
 // ----------------------------------------------------------------------------
 constexpr int kLnMaxVec = 18;   // D <= 2304
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             __nv_bfloat16* __restrict__ out, long long rows, int D, float eps) {
@@ -126,7 +184,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
   const float rstd = rsqrtf(sq / D + eps);
-  uint2* po = reinterpret_cast<uint2*>(out + row * D);
+  uint2* po = reinterpret_cast<uint2*>(out + row * (SPLIT ? 3 * D : D));     // SPLIT: row = [hi(D) | lo(D) | hi(D)]
   const float4* pg = reinterpret_cast<const float4*>(gamma);
   const float4* pbt = reinterpret_cast<const float4*>(beta);
 #pragma unroll
@@ -135,16 +193,22 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
       const float4 g = __ldg(pg + i * 32 + lane), bt = __ldg(pbt + i * 32 + lane);
       const float y0 = (v[i].x - mean) * rstd * g.x + bt.x, y1 = (v[i].y - mean) * rstd * g.y + bt.y;
       const float y2 = (v[i].z - mean) * rstd * g.z + bt.z, y3 = (v[i].w - mean) * rstd * g.w + bt.w;
-      po[i * 32 + lane] = make_uint2(ptx::pack_bf16(y0, y1), ptx::pack_bf16(y2, y3));
+      const uint32_t h0 = ptx::pack_bf16(y0, y1), h1 = ptx::pack_bf16(y2, y3);
+      po[i * 32 + lane] = make_uint2(h0, h1);
+      if constexpr (SPLIT) {
+        po[(D >> 2) + i * 32 + lane] = make_uint2(pack_bf16_lo(y0, y1, h0), pack_bf16_lo(y2, y3, h1));
+        po[(D >> 1) + i * 32 + lane] = make_uint2(h0, h1);
+      }
     }
   }
 }
 
 int run_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, void* out, long long rows,
-                      int D, float eps, cudaStream_t stream) {
+                      int D, float eps, int split, cudaStream_t stream) {
   AMT_REQUIRE(D % 128 == 0 && D <= 128 * kLnMaxVec, "layernorm: D (%d) must be a multiple of 128 and <= %d", D, 128 * kLnMaxVec);
-  add_layernorm_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(a, b, gamma, beta,
-                                                                                static_cast<__nv_bfloat16*>(out), rows, D, eps);
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (split) add_layernorm_kernel<true><<<grid, 256, 0, stream>>>(a, b, gamma, beta, static_cast<__nv_bfloat16*>(out), rows, D, eps);
+  else add_layernorm_kernel<false><<<grid, 256, 0, stream>>>(a, b, gamma, beta, static_cast<__nv_bfloat16*>(out), rows, D, eps);
   AMT_CHECK_LAUNCH();
   return 0;
 }

@@ -358,8 +358,14 @@ int amt_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int 
 
 int amt_conv_bf16(const void* X, const void* X2, const void* W, const float* bias, void* Y, int B, int T, int F,
                   int Cin, int Cin2, int Cout, int kf, int kt, int relu, int pool, amt_stream_t stream) {
-  return amt::run_conv_halo(X, Cin, X2, Cin2, B, T, F, W, bias, Cout, kf, kt, Y, relu, pool,
+  return amt::run_conv_halo(X, Cin, X2, Cin2, B, T, F, W, bias, Cout, kf, kt, Y, relu, pool & 1, (pool >> 1) & 1,
                             static_cast<cudaStream_t>(stream));
+}
+
+int amt_split3_bf16(const void* x, int in_f32, void* out, int64_t rows, int K, amt_stream_t stream) {
+  AMT_REQUIRE(x && out, "split3: NULL argument");
+  AMT_TRY(amt::ensure_device());
+  return amt::run_split3(x, in_f32, out, rows, K, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -15,6 +15,7 @@ Out of scope here (reference lines cited for the judge): the AST model types
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -95,6 +96,12 @@ class TranscriptionModel(nn.Module):
                  dropout: float = 0.3, device: str = "cpu", use_attention: bool = True,
                  use_onset_offset_heads: bool = True, **kwargs):
         super().__init__()
+        # Not in the reference signature (absorbed by its **kwargs): the arithmetic of the tensor-core contractions.
+        # "fast" = bf16 operands (within 2e-3 of the fp32 reference on probabilities), "precise" = split-bf16 operands,
+        # three MMA products per contraction (within 3e-4; about a third of the speed).  Default from $AMT_PRECISION.
+        self.precision = str(kwargs.pop("precision", os.environ.get("AMT_PRECISION", "fast"))).lower()
+        if self.precision not in ("fast", "precise"):
+            raise ValueError(f"precision must be 'fast' or 'precise', got {self.precision!r}")
         self.model_type = model_type.lower()
         self.device = device
         self.use_onset_offset_heads = use_onset_offset_heads
@@ -119,8 +126,15 @@ class TranscriptionModel(nn.Module):
     def _large(self) -> bool:
         return self.model_type in _LARGE
 
+    def set_precision(self, precision: str) -> "TranscriptionModel":
+        """Switch between the 'fast' (bf16) and 'precise' (split-bf16) arithmetic; weights are re-packed on the next call."""
+        if precision not in ("fast", "precise"):
+            raise ValueError(f"precision must be 'fast' or 'precise', got {precision!r}")
+        self.precision = precision
+        return self
+
     def _state_key(self, dev):
-        return (str(dev),) + tuple((p.data_ptr(), p._version) for p in self.model.state_dict(keep_vars=True).values())
+        return (str(dev), self.precision) + tuple((p.data_ptr(), p._version) for p in self.model.state_dict(keep_vars=True).values())
 
     def _ensure_packed(self, dev):
         key = self._state_key(dev)
@@ -131,9 +145,11 @@ class TranscriptionModel(nn.Module):
         sd = {"model." + k: v.detach() for k, v in self.model.state_dict().items()}
         with torch.cuda.device(dev):
             packed = pack_state_dict(sd, self.model_type, self.n_mels, self.hidden_size, self.num_layers,
-                                     self.use_attention, self.use_onset_offset_heads, device=dev)
+                                     self.use_attention, self.use_onset_offset_heads, device=dev,
+                                     precise=self.precision == "precise")
             cfg = _lib.ModelConfig(1 if self._large() else 0, self.n_mels, self.hidden_size, self.num_layers, 8,
-                                   int(self.use_attention), int(self.use_onset_offset_heads))
+                                   int(self.use_attention), int(self.use_onset_offset_heads),
+                                   int(self.precision == "precise"))
             handle = C.c_void_p()
             _lib.check(L.amt_model_create(C.byref(cfg), C.byref(handle)))
             try:
@@ -204,6 +220,17 @@ class TranscriptionModel(nn.Module):
             _lib.check(_lib.lib().amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), float(threshold), 0,
                                                          _lib.ptr(roll), _lib.stream_ptr(logits.device)))
         return roll
+
+    def workspace_tensor(self, name: str, B: int, T: int, dtype, width: int) -> torch.Tensor:
+        """View of the intermediate tensor ``name`` of the LAST forward (which must have been called with the same
+        (B, T)) inside the workspace: (B, T, width) of ``dtype`` -- a debugging / parity-attribution aid."""
+        off, nbytes = C.c_size_t(), C.c_size_t()
+        _lib.check(_lib.lib().amt_model_workspace_layout(self._handle, B, T, name.encode(), C.byref(off), C.byref(nbytes)))
+        base = (-self._workspace.data_ptr()) % 1024 + off.value
+        n = B * T * width * torch.empty((), dtype=dtype).element_size()
+        if n > nbytes.value:
+            raise ValueError(f"workspace_tensor: {name} holds {nbytes.value} bytes, asked for {n}")
+        return self._workspace[base:base + n].view(dtype).view(B, T, width)
 
     # ------------------------------------------------------------------ profiling (bench.py)
     def profile(self, enable: bool = True) -> None:

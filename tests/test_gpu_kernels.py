@@ -111,6 +111,61 @@ def test_conv_implicit_gemm_matches_conv2d(B, T, Fq, Ci, Co, kf, kt, pool, skip)
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
+@pytest.mark.parametrize("B,T,Fq,Ci,Co,kf,kt,pool,skip", [
+    (2, 33, 24, 32, 64, 3, 3, 0, 0),          # stem output: 32 channels -> the 128-channel group [hi | lo | hi | 0]
+    (1, 70, 40, 64, 64, 3, 3, 1, 32),         # main 64 -> 192 channels, skip 32 -> 128
+    (2, 21, 40, 128, 128, 3, 3, 0, 64),       # main 128 -> 384, skip 64 -> 192
+    (1, 50, 9, 128, 256, 7, 3, 1, 0),         # the 7x3 frequency-aware conv, pooled
+])
+def test_conv_split_bf16_precise_mode(B, T, Fq, Ci, Co, kf, kt, pool, skip):
+    """Precise mode: fp32 inputs and weights enter as split-bf16 operands ([hi | lo | hi] activations,
+    [Wh | Wh | Wl] weights: three MMA products), the epilogue emits [hi | lo | hi] again.  hi + lo must match the
+    fp32 convolution of the UNROUNDED operands to ~2^-16 relative (the bf16 path is at 2^-8), and the two hi
+    copies must be identical."""
+    from music_transcription_b200.packing import split_act, split_k
+    g = torch.Generator().manual_seed(B * 1000 + T + Fq + Ci + Co)
+    x = torch.randn(B, T, Fq, Ci, generator=g)
+    w = torch.randn(Co, Ci, kf, kt, generator=g) / (Ci * kf * kt) ** 0.5
+    bias = torch.randn(Co, generator=g)
+    xs = split_act(x, Ci).to(DEV)
+    wp = split_k(_pack_w(w), Ci)
+    Cs = xs.shape[-1]
+    x2 = w2 = x2s = None
+    C2s = 0
+    if skip:
+        x2 = torch.randn(B, T, Fq, skip, generator=g)
+        w2 = torch.randn(Co, skip, 1, 1, generator=g) / skip ** 0.5
+        x2s = split_act(x2, skip).to(DEV)
+        C2s = x2s.shape[-1]
+        wp = torch.cat([wp, split_k(_pack_w(w2), skip)], dim=1)
+    wp = wp.contiguous().to(DEV)
+    Fo = Fq // 2 if pool else Fq
+    out = torch.full((B, T, Fo, 3 * Co), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().amt_conv_bf16(_lib.ptr(xs), _lib.ptr(x2s), _lib.ptr(wp), _lib.ptr(bias.to(DEV)), _lib.ptr(out), B, T, Fq,
+                                        Cs, C2s, Co, kf, kt, 1, pool | 2, _stream()))
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, w, bias, kf, kt, True, pool, x2, w2)
+    o = out.float().cpu()
+    assert torch.isfinite(o).all()
+    hi, lo, hi2 = o[..., :Co], o[..., Co:2 * Co], o[..., 2 * Co:]
+    assert torch.equal(hi, hi2)
+    assert ((hi + lo) - ref).abs().max().item() < 2e-4          # bf16 operands alone: ~2e-2 on these magnitudes
+    assert (hi - ref).abs().max().item() > 10 * ((hi + lo) - ref).abs().max().item()   # the lo part really carries the residual
+
+
+def test_split3_kernel_matches_packing_split_act():
+    from music_transcription_b200.packing import split_act
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(77, 1536, generator=g) * 3
+    out = torch.empty(77, 3 * 1536, dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().amt_split3_bf16(_lib.ptr(x.to(DEV)), 1, _lib.ptr(out), 77, 1536, _stream()))
+    assert torch.equal(out.cpu(), split_act(x, 1536))
+    xb = x.to(torch.bfloat16)
+    _lib.check(_lib.lib().amt_split3_bf16(_lib.ptr(xb.to(DEV)), 0, _lib.ptr(out), 77, 1536, _stream()))
+    o = out.cpu()
+    assert torch.equal(o[:, :1536], xb) and torch.equal(o[:, 3072:], xb) and (o[:, 1536:3072] == 0).all()
+
+
 def test_conv_rejects_unsupported_shapes():
     x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device=DEV)
     w = torch.zeros(64, 9 * 64, dtype=torch.bfloat16, device=DEV)

@@ -2,10 +2,14 @@
 TranscriptionModel (CUDA kernels through the C ABI) vs the oracle fp32 forward and vs the
 golden outputs of the real reference, and the batched audio->notes pipeline.
 
-Stated tolerances (bf16 tensor-core operands, fp32 accumulation; SURVEY.md 7.2-2 measured a
-5.2e-3 probability floor for bf16-rounded weights alone):
-    log-mel  : max-abs <= 2e-2 dB, mean-abs <= 5e-4 dB vs the fp64-FFT oracle (fp32 FFT on the GPU)
-    logits   : max-abs <= 0.2, probabilities max-abs <= 4e-2, mean-abs <= 4e-3 on the stress
+Stated tolerances (measured values + ~20 %, profiles/r2_parity.md):
+    log-mel  : max-abs <= 3e-3 dB, mean-abs <= 1e-4 dB vs the fp64-FFT oracle (fp32 FFT on the GPU)
+    canonical config (n_mels 320 / hidden 512 / 3 layers, default-init-scale weights), vs the REAL reference's outputs:
+               fast mode (bf16 operands, fp32 accumulation)  probabilities max-abs <= 2e-3, mean <= 3.5e-4, <= 0.4 % cells flip
+               precise mode (split-bf16 operands)            probabilities max-abs <= 4e-4, mean <= 8e-5,   <= 0.1 % cells flip
+               (tests/attribution.py: the fast-mode distance is the bf16 operand floor, spread evenly over the conv
+               stack, the input projections and the heads; the recurrence contributes < 1e-4)
+    logits   : max-abs <= 0.15, probabilities max-abs <= 3e-2, mean-abs <= 3e-3 on the stress
                checkpoints of synth.synth_state_dict (unit-gain weights, perturbed BatchNorm: logits
                reach +-3); a CPU emulation of the same bf16 roundings (tests/emulate.py) shows this is
                the bf16 operand floor (0.13 / 2.4e-2 / 2.5e-3), not kernel error -- the kernels
@@ -27,7 +31,7 @@ DEV = "cuda:0"
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 LOGMEL_MAX_DB, LOGMEL_MEAN_DB = 3e-3, 1e-4          # dB, vs the fp64-FFT oracle (measured: <= 1.5e-3 max, <= 2.5e-5 mean)
-LOGIT_MAX, PROB_MAX, PROB_MEAN = 0.2, 4e-2, 4e-3
+LOGIT_MAX, PROB_MAX, PROB_MEAN = 0.15, 3e-2, 3e-3      # stress checkpoints; measured 0.124 / 2.36e-2 / 2.46e-3 (profiles/r2_parity.md)
 
 
 def test_frontend_filterbank_matches_oracle():
@@ -104,6 +108,7 @@ def test_model_matches_reference_golden(path):
         ref = torch.from_numpy(g[k])
         dl = (v.cpu() - ref).abs()
         dp = (torch.sigmoid(v.cpu()) - torch.sigmoid(ref)).abs()
+        _report(f"fast.{os.path.basename(path)[6:-4]}.{k}", prob_max=dp.max(), prob_mean=dp.mean(), logit_max=dl.max())
         assert dl.max() < LOGIT_MAX and dp.max() < PROB_MAX and dp.mean() < PROB_MEAN, (k, dl.max(), dp.max(), dp.mean())
     # kernels vs a CPU emulation of the same bf16 roundings: isolates kernel error from the bf16 floor
     from music_transcription_b200.packing import pack_state_dict
@@ -116,7 +121,9 @@ def test_model_matches_reference_golden(path):
         assert dl.max() < 5e-2 and dp.max() < 1e-2 and dp.mean() < 1e-3, ("emu", k, dl.max(), dp.max(), dp.mean())
     pred = m.predict(x, threshold=0.5)
     assert pred.shape == g["pred"].shape and set(np.unique(pred.cpu().numpy())) <= {0.0, 1.0}
-    assert (pred.cpu().numpy() != g["pred"]).mean() < 0.02
+    flips = (pred.cpu().numpy() != g["pred"]).mean()
+    _report(f"fast.{os.path.basename(path)[6:-4]}.pred", flips=flips)
+    assert flips < 0.02
 
 
 def test_stage_profile_and_in_flight_query():
@@ -178,7 +185,7 @@ def test_canonical_large_model_vs_oracle_full_chunk():
     """CNNRNNModelLarge at the reference's canonical config (n_mels 320, hidden 512, 3 layers), 30-s
     chunks of real log-mel; oracle = fp32 PyTorch restatement on the CPU.
     (a) default-init-scale weights (gain 1/sqrt(3) == torch's kaiming/LSTM default variance): the stated
-        product tolerance, probabilities max-abs <= 1.5e-2;
+        product tolerance of the fast mode, probabilities max-abs <= 2e-3 (the bf16 operand floor, tests/attribution.py);
     (b) stress weights (unit gain, logits +-3, chaotic LSTM dynamics): the kernels must match a CPU
         emulation of the same bf16 roundings to 5e-2 / 1e-2 / 1e-3, and stay within 1.25x of that
         emulation's own distance to the fp32 oracle (chunk 3 has a measured bf16 floor of 0.35 logits)."""
@@ -197,7 +204,8 @@ def test_canonical_large_model_vs_oracle_full_chunk():
     for k in ("frame", "onset", "offset"):
         dl = (out[k].cpu() - ref[k]).abs()
         dp = (torch.sigmoid(out[k].cpu()) - torch.sigmoid(ref[k])).abs()
-        assert dl.max() < 6e-2 and dp.max() < 1.5e-2 and dp.mean() < 2e-3, ("default-init", k, dl.max(), dp.max(), dp.mean())
+        _report(f"canon_vs_oracle.{k}", prob_max=dp.max(), prob_mean=dp.mean(), logit_max=dl.max())
+        assert dp.max() < CANON_PROB_MAX and dp.mean() < CANON_PROB_MEAN, ("default-init", k, dl.max(), dp.max(), dp.mean())
     # (b)
     sd = synth.synth_state_dict("cnn_rnn_large", 320, 512, 3, seed=1)
     m.load_state_dict(sd)           # in-place update -> repacked on the next call
@@ -225,7 +233,7 @@ def _report(name, **vals):
             f.write(json.dumps({"test": name, **{k: float(v) for k, v in vals.items()}}) + "\n")
 
 
-CANON_PROB_MAX, CANON_PROB_MEAN, CANON_FLIPS = 4e-3, 6e-4, 5e-3      # fast (bf16) mode; measured values in profiles/r2_parity.md
+CANON_PROB_MAX, CANON_PROB_MEAN, CANON_FLIPS = 2e-3, 3.5e-4, 4e-3    # fast (bf16) mode; measured 1.55e-3 / 2.6e-4 / 2.8e-3 (profiles/r2_parity.md)
 
 
 @pytest.mark.parametrize("name", ["large", "small"])
@@ -251,6 +259,56 @@ def test_canonical_shape_goldens_from_the_real_reference(name):
         flips = ((v.cpu() > 0) != (ref > 0)).float().mean()
         _report(f"canon_{name}.{k}", prob_max=dp.max(), prob_mean=dp.mean(), logit_max=(v.cpu() - ref).abs().max(), flips=flips)
         assert dp.max() < CANON_PROB_MAX and dp.mean() < CANON_PROB_MEAN and flips < CANON_FLIPS, (k, dp.max(), dp.mean(), flips)
+
+
+PRECISE_PROB_MAX, PRECISE_PROB_MEAN, PRECISE_FLIPS = 4e-4, 8e-5, 1e-3     # precise (split-bf16) mode; measured: profiles/r2_parity.md
+
+
+@pytest.mark.parametrize("name", ["large", "small"])
+def test_precise_mode_matches_the_real_reference_at_canonical_shapes(name):
+    """precision="precise": split-bf16 operands (three MMA products per contraction).  Against the outputs of the
+    unmodified fp32 reference at the canonical shapes: probabilities within 4e-4 (north_star's example tolerance is
+    1e-3), fewer than 0.1 % thresholded cells differ.  What remains is the recurrence (bf16 W_hh / h feedback,
+    tanh.approx) and the attention core (bf16 q, k, v, P) -- tests/attribution.py predicts 2e-4."""
+    g = np.load(os.path.join(GOLDEN, f"canon_{name}.npz"))
+    n_mels, H, L, B, T, seed = [int(v) for v in g["cfg"]]
+    mt = str(g["model_type"])
+    sd = synth.synth_state_dict(mt, n_mels, H, L, seed=seed, gain=float(g["gain"]))
+    m = TranscriptionModel(mt, n_mels=n_mels, hidden_size=H, num_layers=L, dropout=0.2, device=DEV, precision="precise")
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x = torch.from_numpy(g["x"].astype(np.float32)).to(DEV)
+    out = m(x, return_all_heads=True)
+    out = out if isinstance(out, dict) else {"frame": out}
+    for k, v in out.items():
+        ref = torch.from_numpy(g[k])
+        dp = (torch.sigmoid(v.cpu()) - torch.sigmoid(ref)).abs()
+        flips = ((v.cpu() > 0) != (ref > 0)).float().mean()
+        _report(f"precise.canon_{name}.{k}", prob_max=dp.max(), prob_mean=dp.mean(), logit_max=(v.cpu() - ref).abs().max(), flips=flips)
+        assert dp.max() < PRECISE_PROB_MAX and dp.mean() < PRECISE_PROB_MEAN and flips < PRECISE_FLIPS, (k, dp.max(), dp.mean(), flips)
+    # switching the same object back to fast mode re-packs and reproduces the fast result
+    fast = TranscriptionModel(mt, n_mels=n_mels, hidden_size=H, num_layers=L, dropout=0.2, device=DEV)
+    fast.load_state_dict(sd)
+    assert torch.equal(m.set_precision("fast")(x), fast(x))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "model_*_*.npz"))),
+                         ids=lambda p: os.path.basename(p)[6:-4])
+def test_precise_mode_on_the_small_reference_goldens(path):
+    """The six reference-run fixtures (unit-gain stress weights, odd n_mels, no attention / no heads) in precise mode:
+    one order of magnitude inside the fast-mode tolerance."""
+    g, mt, n_mels, H, L, attn, heads, sd = _load_case(path)
+    m = TranscriptionModel(model_type=mt, n_mels=n_mels, hidden_size=H, num_layers=L, dropout=0.2, device=DEV,
+                           use_attention=attn, use_onset_offset_heads=heads, precision="precise")
+    m.load_state_dict(sd, strict=True)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    got = m(x, return_all_heads=True) if (mt.endswith("large") and heads) else {"frame": m(x)}
+    for k, v in got.items():
+        ref = torch.from_numpy(g[k])
+        dl = (v.cpu() - ref).abs()
+        dp = (torch.sigmoid(v.cpu()) - torch.sigmoid(ref)).abs()
+        _report(f"precise.{os.path.basename(path)[6:-4]}.{k}", prob_max=dp.max(), prob_mean=dp.mean(), logit_max=dl.max())
+        assert dl.max() < LOGIT_MAX / 8 and dp.max() < PROB_MAX / 8 and dp.mean() < PROB_MEAN / 8, (k, dl.max(), dp.max(), dp.mean())
 
 
 @pytest.mark.parametrize("B", [16, 64])
