@@ -19,10 +19,9 @@ import torch
 from . import _lib
 
 
-def f1_counts(probs: torch.Tensor, target: torch.Tensor, lengths, thresholds) -> np.ndarray:
-    """probs/target (n_pieces, 88, T) CUDA float32, lengths (n_pieces,), thresholds: any order /
-    duplicates allowed (float64 as np.arange yields them).  Returns int64 [n_pieces, n_thr, 3]
-    = (TP, FP, FN) per piece and threshold, compare ``probs > float32(threshold)``."""
+def f1_counts_device(probs: torch.Tensor, target: torch.Tensor, lengths, thresholds) -> torch.Tensor:
+    """Launch-only form of ``f1_counts``: returns the int64 [n_pieces, n_thr, 3] table as a CUDA tensor without a host
+    synchronisation (all launches on the current stream), so sweeps over many pieces / ranks pay one D2H at the end."""
     _lib.require_cuda(probs, "f1_counts probs")
     dev = probs.device
     probs = probs.float().contiguous()
@@ -31,20 +30,31 @@ def f1_counts(probs: torch.Tensor, target: torch.Tensor, lengths, thresholds) ->
     thr64 = np.asarray(list(thresholds), dtype=np.float64).reshape(-1)
     thr32 = thr64.astype(np.float32)                       # torch compares in float32
     uniq, inverse = np.unique(thr32, return_inverse=True)  # sorted ascending
-    out = np.zeros((n_pieces, len(uniq), 3), dtype=np.int64)
-    lengths_t = torch.as_tensor(np.asarray(lengths, dtype=np.int32)).to(dev)
+    lengths_t = lengths.to(dev, torch.int32) if torch.is_tensor(lengths) else torch.as_tensor(np.asarray(lengths, dtype=np.int32)).to(dev)
+    out = torch.empty(n_pieces, len(uniq), 3, dtype=torch.int64, device=dev)
     L = _lib.lib()
     with torch.cuda.device(dev):
         for j0 in range(0, len(uniq), 512):
-            chunk = torch.from_numpy(uniq[j0:j0 + 512].copy()).to(dev)
+            chunk = torch.from_numpy(uniq[j0:j0 + 512].copy()).to(dev, non_blocking=True)
+            one_block = len(uniq) <= 512
             for p0 in range(0, n_pieces, 65535):
                 p1 = min(n_pieces, p0 + 65535)
-                res = torch.empty(p1 - p0, len(chunk), 3, dtype=torch.int64, device=dev)
+                res = out[p0:p1] if one_block else torch.empty(p1 - p0, len(chunk), 3, dtype=torch.int64, device=dev)
                 _lib.check(L.amt_f1_counts(_lib.ptr(probs[p0:p1]), _lib.ptr(target[p0:p1]), _lib.ptr(lengths_t[p0:p1]),
                                            p1 - p0, n_pitch, T, _lib.ptr(chunk), len(chunk), _lib.ptr(res),
                                            _lib.stream_ptr(dev)))
-                out[p0:p1, j0:j0 + len(chunk)] = res.cpu().numpy()
-    return out[:, inverse]
+                if not one_block:
+                    out[p0:p1, j0:j0 + len(chunk)] = res
+    if len(inverse) == len(uniq) and np.array_equal(inverse, np.arange(len(uniq))):
+        return out
+    return out[:, torch.from_numpy(inverse.astype(np.int64)).to(dev)]
+
+
+def f1_counts(probs: torch.Tensor, target: torch.Tensor, lengths, thresholds) -> np.ndarray:
+    """probs/target (n_pieces, 88, T) CUDA float32, lengths (n_pieces,), thresholds: any order /
+    duplicates allowed (float64 as np.arange yields them).  Returns int64 [n_pieces, n_thr, 3]
+    = (TP, FP, FN) per piece and threshold, compare ``probs > float32(threshold)``.  One host sync (the final D2H)."""
+    return f1_counts_device(probs, target, lengths, thresholds).cpu().numpy()
 
 
 def f1_from_counts(counts: np.ndarray) -> np.ndarray:

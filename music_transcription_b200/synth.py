@@ -46,6 +46,30 @@ def piano_chord_batch(ks, n_samples: int = CHUNK_SAMPLES) -> np.ndarray:
     return np.stack([piano_chord(int(k), n_samples) for k in ks])
 
 
+def piano_chord_batch_fast(ks, n_samples: int = CHUNK_SAMPLES, sr: int = SR) -> torch.Tensor:
+    """``piano_chord`` for many chunks, evaluated with torch's multi-threaded float64 kernels in the same operation
+    order (the float32 results are bit-identical to ``piano_chord``, tests/test_packing.py): 240 chunks in ~15 s
+    instead of 70.  Returns a float32 CPU tensor (len(ks), n_samples)."""
+    ks = [int(k) for k in ks]
+    out = torch.empty(len(ks), n_samples, dtype=torch.float32)
+    t = torch.arange(n_samples, dtype=torch.float64) / sr
+    env = torch.exp(-1.5 * torch.remainder(t, 2.0))
+    for i, k in enumerate(ks):
+        rng = np.random.default_rng(k)
+        y = torch.zeros(n_samples, dtype=torch.float64)
+        for midi in (60, 64, 67, 72):
+            f0 = 440.0 * 2.0 ** ((midi + (k % 12) - 69) / 12.0)
+            for h in range(1, 6):
+                y += (0.5 / h) * torch.sin(2.0 * np.pi * f0 * h * t) * env
+        out[i] = (0.2 * y + 1e-3 * torch.from_numpy(rng.standard_normal(n_samples))).float()
+    return out
+
+
+def to_pcm16(wav: torch.Tensor) -> torch.Tensor:
+    """float waveform in [-1, 1) -> the int16 samples a 16-bit WAVE file of it holds (round to nearest, saturate)."""
+    return torch.clamp(torch.round(wav * 32768.0), -32768, 32767).to(torch.int16)
+
+
 def cheap_wave_batch(n: int, n_samples: int = CHUNK_SAMPLES, seed: int = 0) -> torch.Tensor:
     """Fast batch generator for bench.py (tones + noise, float32 CPU tensor).
     Same spectral character as ``piano_chord`` but vectorised in torch so that

@@ -30,14 +30,20 @@ def _pool_f(x):
     return F.max_pool2d(x, kernel_size=(2, 1))
 
 
-def _bilstm(x, sd, prefix, hidden, layers):
+def _bilstm(x, sd, prefix, hidden, layers, cache=None):
     """nn.LSTM(batch_first=True, bidirectional=True) in eval mode, fp32
-    (reference cnn_rnn_model.py:45-52,212-228; inter-layer dropout is off)."""
+    (reference cnn_rnn_model.py:45-52,212-228; inter-layer dropout is off).  ``cache``: a dict that keeps the built
+    module between calls -- the reference builds its modules once (main.py:41-54), so a timed loop must too."""
     inp = x.shape[-1]
-    rnn = torch.nn.LSTM(inp, hidden, num_layers=layers, batch_first=True, bidirectional=True).to(x.device)
-    own = rnn.state_dict()
-    rnn.load_state_dict({k: sd[prefix + "." + k] for k in own})
-    rnn.eval()
+    key = (prefix, str(x.device))
+    rnn = cache.get(key) if cache is not None else None
+    if rnn is None:
+        rnn = torch.nn.LSTM(inp, hidden, num_layers=layers, batch_first=True, bidirectional=True).to(x.device)
+        own = rnn.state_dict()
+        rnn.load_state_dict({k: sd[prefix + "." + k] for k in own})
+        rnn.eval()
+        if cache is not None:
+            cache[key] = rnn
     out, _ = rnn(x.float())
     return out
 
@@ -57,15 +63,14 @@ def _features(x):
 
 
 @torch.no_grad()
-def small_forward(sd, x, hidden_size, num_layers):
+def small_forward(sd, x, hidden_size, num_layers, lstm_cache=None):
     """CNNRNNModel.forward (reference cnn_rnn_model.py:57-74): (B,1,F,T)->(B,88,T)."""
-    sd = {k: v.float() if v.is_floating_point() else v for k, v in sd.items()}
     h = _pool_f(F.relu(_conv_bn(x, sd, "model.cnn.0", "model.cnn.1", (1, 1))))
     h = _pool_f(F.relu(_conv_bn(h, sd, "model.cnn.4", "model.cnn.5", (1, 1))))
     feats = _features(h)
     if feats.shape[1] == 0:
         return torch.zeros(x.shape[0], 88, 1)
-    r = _bilstm(feats, sd, "model.rnn", hidden_size, num_layers)
+    r = _bilstm(feats, sd, "model.rnn", hidden_size, num_layers, lstm_cache)
     return F.linear(r, sd["model.fc.weight"], sd["model.fc.bias"]).transpose(1, 2)
 
 
@@ -85,9 +90,8 @@ def _attention(x, sd, num_heads=8, clip=10.0):
 
 @torch.no_grad()
 def large_forward(sd, x, hidden_size, num_layers, use_attention=True,
-                  use_onset_offset_heads=True, return_all_heads=False, return_internals=False):
-    """CNNRNNModelLarge.forward (reference cnn_rnn_model.py:262-349)."""
-    sd = {k: v.float() if v.is_floating_point() else v for k, v in sd.items()}
+                  use_onset_offset_heads=True, return_all_heads=False, return_internals=False, lstm_cache=None):
+    """CNNRNNModelLarge.forward (reference cnn_rnn_model.py:262-349).  The checkpoint must be fp32 (as the reference's is)."""
     B = x.shape[0]
     internals = {}
     h = _pool_f(F.relu(_conv_bn(x, sd, "model.conv1.0", "model.conv1.1", (1, 1))))
@@ -104,8 +108,8 @@ def large_forward(sd, x, hidden_size, num_layers, use_attention=True,
         if use_onset_offset_heads and return_all_heads:
             return {"frame": z, "onset": z.clone(), "offset": z.clone()}
         return z
-    main = _bilstm(feats, sd, "model.rnn_main", hidden_size, num_layers)
-    local = _bilstm(feats, sd, "model.rnn_local", hidden_size // 2, 1)
+    main = _bilstm(feats, sd, "model.rnn_main", hidden_size, num_layers, lstm_cache)
+    local = _bilstm(feats, sd, "model.rnn_local", hidden_size // 2, 1, lstm_cache)
     r = torch.cat([main, local], dim=-1)
     internals["rnn"] = r
     if use_attention:

@@ -39,3 +39,33 @@ def test_packed_emulation_matches_reference(path):
         dp = (torch.sigmoid(v) - torch.sigmoid(ref)).abs()
         # bf16 weights + bf16 activations: same tolerance the GPU tests state
         assert dl < 0.2 and dp.max().item() < 4e-2 and dp.mean().item() < 4e-3, (k, dl, dp.max().item())
+
+
+def test_fast_chord_batch_is_the_survey_recipe_and_pcm16_round_trip():
+    ks = [0, 7, 13]
+    fast = synth.piano_chord_batch_fast(ks, n_samples=20000)
+    for i, k in enumerate(ks):
+        assert np.array_equal(fast[i].numpy(), synth.piano_chord(k, n_samples=20000))
+    pcm = synth.to_pcm16(fast)
+    assert pcm.dtype == torch.int16 and (pcm.float() / 32768.0 - fast).abs().max() <= 0.5 / 32768 + 1e-9
+
+
+def test_precise_packing_reconstructs_fp32_weights():
+    """precise=True: every contraction weight is [Wh | Wh | Wl] per channel group; Wh + Wl must reproduce the fp32
+    packed weight to 2^-16 relative, and the group structure must match split_act's [hi | lo | hi (| 0)]."""
+    from music_transcription_b200.packing import split_act, split_k
+    sd = synth.synth_state_dict("cnn_rnn_large", 64, 128, 2, seed=3)
+    fast = pack_state_dict(sd, "cnn_rnn_large", 64, 128, 2, weight_dtype=torch.float32)
+    prec = pack_state_dict(sd, "cnn_rnn_large", 64, 128, 2, precise=True)
+    # x . w  ==  split_act(x) . split_k(w)  up to the dropped lo*lo term, for both group shapes
+    g = torch.Generator().manual_seed(0)
+    for group, k in ((32, 96), (64, 128), (256, 256)):
+        w, x = torch.randn(5, k, generator=g), torch.randn(3, k, generator=g)
+        got = split_act(x, group).double() @ split_k(w, group).double().t()
+        assert (got - x.double() @ w.double().t()).abs().max() < 4 * k ** 0.5 * 2 ** -16      # bf16 alone: ~k^0.5 * 2^-8
+    assert prec["rnn0.whh0"].shape == fast["rnn0.whh0"].shape            # recurrent weights stay plain bf16
+    w = prec["attn.qkv.w"].float()
+    K = fast["attn.qkv.w"].shape[1]
+    assert w.shape[1] == 3 * K and torch.equal(w[:, :K], w[:, K:2 * K])
+    assert ((w[:, :K] + w[:, 2 * K:]) - fast["attn.qkv.w"]).abs().max() < 2 ** -16
+    assert prec["res1.c1.w"].shape[1] == 9 * 128 and prec["res1.c2.w"].shape[1] == 9 * 192 + 128
