@@ -99,6 +99,18 @@ int amt_model_destroy(amt_model* m);
 int amt_model_set_tensor(amt_model* m, const char* name, const void* dev_ptr, size_t nbytes);
 /* Verifies every tensor the configuration needs is present with the right size. */
 int amt_model_finalize(amt_model* m);
+/* Load a reference checkpoint: the n tensors of TranscriptionModel.state_dict() (reference models/cnn_rnn_model.py:28-55,
+ * :179-260; keys as torch.save writes them, e.g. "model.res_block1.conv1.weight") given as DEVICE pointers to contiguous
+ * float32 data with their element counts.  The library packs them on the device into memory owned by the handle -- eval
+ * BatchNorm folded into the convolutions, (kf, kt, cin) K order with the residual 1x1 skip conv appended, slice-ordered
+ * LSTM gate rows, b_ih + b_hh, permuted layer-0 columns, stacked + padded heads, bf16 (or the split-bf16 layout of
+ * AMT_PRECISION_PRECISE) -- and finalizes the handle.  Integer tensors (num_batches_tracked) and unknown keys are
+ * ignored; a missing or mis-sized tensor is AMT_ERR_STATE.  The sources are borrowed only until the call returns (it
+ * synchronises `stream`).  Replaces amt_model_set_tensor + amt_model_finalize for hosts without the Python packer. */
+int amt_model_load(amt_model* m, const char* const* names, const void* const* ptrs, const int64_t* numels, int n,
+                   amt_stream_t stream);
+/* The packed tensor registered under `name` ("res1.c2.w", "rnn0.wih", ... -- DESIGN.md "Packed weights"). */
+int amt_model_get_tensor(const amt_model* m, const char* name, const void** dev_ptr, size_t* nbytes);
 size_t amt_model_workspace_bytes(const amt_model* m, int B, int T);
 /* Where an intermediate tensor of amt_model_forward(m, ., B, T, ...) lives inside the caller's workspace: byte offset
  * and extent of buffer `name` ("act1", "feat", "gx", "seq_a", "seq_b", "rnn_f32", "qkv", "att", "proj", "normed",

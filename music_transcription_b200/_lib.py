@@ -52,6 +52,8 @@ _SIGS = {
     "amt_model_destroy": (C.c_int, [C.c_void_p]),
     "amt_model_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
     "amt_model_finalize": (C.c_int, [C.c_void_p]),
+    "amt_model_load": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
+    "amt_model_get_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "amt_model_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "amt_model_workspace_layout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "amt_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

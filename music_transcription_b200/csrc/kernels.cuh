@@ -1,5 +1,7 @@
 // Internal (non-ABI) launch entry points shared between translation units.
 #pragma once
+#include <string>
+
 #include "common.cuh"
 
 namespace amt {
@@ -22,5 +24,16 @@ int run_add_layernorm(const float* a, const float* b, const float* gamma, const 
 int run_split3(const void* x, int in_f32, void* out, long long rows, int K, cudaStream_t stream);
 int run_heads_transpose(const float* in, int ld, int B, int T, int n_heads, float* o0, float* o1, float* o2,
                         cudaStream_t stream);
+
+// What amt_model_load (model_load.cu) may touch of an amt_model (model.cu)
+struct ModelLoadView {
+  virtual const amt_model_config& cfg() const = 0;
+  virtual size_t expected_bytes() const = 0;                      // sum of the packed tensors' sizes (+ alignment)
+  virtual int alloc_arena(size_t bytes, uint8_t** out) = 0;        // device memory owned by the handle, freed on destroy / reload
+  virtual void set(const std::string& name, void* p, size_t nbytes) = 0;
+  virtual ~ModelLoadView() {}
+};
+int model_load_impl(ModelLoadView* view, const char* const* names, const void* const* ptrs, const int64_t* numels, int n,
+                    cudaStream_t stream);
 
 }  // namespace amt

@@ -68,6 +68,8 @@ struct amt_model {
   amt_model_config cfg;
   std::map<std::string, amt::Tensor> tensors;
   bool finalized = false;
+  void* arena = nullptr;      // packed weights produced by amt_model_load (owned; amt_model_set_tensor pointers are borrowed)
+  int arena_device = -1;
   // derived sizes
   int F1, F2, F3;       // frequency bins after 1, 2, 3 pools
   int Kfeat;            // LSTM input width
@@ -356,8 +358,67 @@ int amt_model_create(const amt_model_config* cfg, amt_model** out) {
   return 0;
 }
 
+static void free_arena(amt_model* m) {
+  if (!m->arena) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != m->arena_device) cudaSetDevice(m->arena_device);
+  cudaFree(m->arena);
+  if (cur != m->arena_device) cudaSetDevice(cur);
+  m->arena = nullptr;
+}
+
 int amt_model_destroy(amt_model* m) {
+  if (m) free_arena(m);
   delete m;
+  return 0;
+}
+
+namespace amt {
+struct LoadView : ModelLoadView {
+  amt_model* m;
+  explicit LoadView(amt_model* mm) : m(mm) {}
+  const amt_model_config& cfg() const override { return m->cfg; }
+  size_t expected_bytes() const override {
+    size_t tot = 0;
+    for (const Expect& e : expected_tensors(*m)) tot += align_up(e.nbytes, 256);
+    return tot;
+  }
+  int alloc_arena(size_t bytes, uint8_t** out) override {
+    free_arena(m);
+    m->tensors.clear();
+    m->finalized = false;
+    AMT_CUDA(cudaGetDevice(&m->arena_device));
+    AMT_CUDA(cudaMalloc(&m->arena, bytes));
+    *out = static_cast<uint8_t*>(m->arena);
+    return 0;
+  }
+  void set(const std::string& name, void* p, size_t nbytes) override { m->tensors[name] = Tensor{p, nbytes}; }
+};
+}  // namespace amt
+
+int amt_model_load(amt_model* m, const char* const* names, const void* const* ptrs, const int64_t* numels, int n,
+                   amt_stream_t stream) {
+  using namespace amt;
+  AMT_REQUIRE(m && names && ptrs && numels && n > 0, "model_load: bad arguments");
+  AMT_TRY(ensure_device());
+  LoadView view(m);
+  const int st = model_load_impl(&view, names, ptrs, numels, n, static_cast<cudaStream_t>(stream));
+  if (st != 0) {
+    free_arena(m);
+    m->tensors.clear();
+    return st;
+  }
+  return amt_model_finalize(m);
+}
+
+int amt_model_get_tensor(const amt_model* m, const char* name, const void** dev_ptr, size_t* nbytes) {
+  using namespace amt;
+  AMT_REQUIRE(m && name && dev_ptr && nbytes, "model_get_tensor: NULL argument");
+  auto it = m->tensors.find(name);
+  if (it == m->tensors.end()) return set_error(AMT_ERR_STATE, "model_get_tensor: no packed tensor '%s'", name);
+  *dev_ptr = it->second.ptr;
+  *nbytes = it->second.nbytes;
   return 0;
 }
 

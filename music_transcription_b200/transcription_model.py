@@ -21,7 +21,6 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .packing import pack_state_dict
 
 _SMALL = ("cnn_rnn", "cnn+rnn")
 _LARGE = ("cnn_rnn_large", "large")
@@ -115,9 +114,19 @@ class TranscriptionModel(nn.Module):
             raise NotImplementedError("the AST/transformer model is outside the B200 hot path (SURVEY.md section 2, row 9)")
         else:
             raise ValueError(f"Unknown model type: {model_type}")
+        # The supported envelope, checked HERE so an unsupported configuration fails at construction with a clear message
+        # (the reference accepts any sizes; the kernels do not -- README "Supported configurations")
+        if hidden_size % 128 != 0 or not 128 <= hidden_size <= 640:
+            raise ValueError(f"hidden_size {hidden_size} unsupported by the sm_100a kernels: a multiple of 128 in 128..640")
+        if self._large() and use_attention and hidden_size > 512:
+            raise ValueError(f"hidden_size {hidden_size} with attention unsupported: head_dim = 3*hidden/8 must be <= 192")
+        if not 1 <= num_layers <= 8:
+            raise ValueError(f"num_layers {num_layers} unsupported (1..8)")
+        if n_mels < (8 if self._large() else 4):
+            raise ValueError(f"n_mels {n_mels} too small for the pooling stack")
+        self._warned_training = False
         self.criterion = nn.BCEWithLogitsLoss()
         self._handle = None          # amt_model*
-        self._packed = None          # name -> device tensor (kept alive while the handle borrows them)
         self._packed_key = None
         self._workspace = None
         self.to(device)
@@ -142,29 +151,43 @@ class TranscriptionModel(nn.Module):
             return
         self._release()
         L = _lib.lib()
-        sd = {"model." + k: v.detach() for k, v in self.model.state_dict().items()}
+        # the checkpoint as the reference stores it (fp32 tensors under their state_dict keys), on the device:
+        # the LIBRARY packs it (amt_model_load: BN fold, layouts, bf16 / split-bf16) -- no torch arithmetic here
+        sd = {"model." + k: v.detach().to(dev, torch.float32).contiguous()
+              for k, v in self.model.state_dict().items() if v.is_floating_point()}
         with torch.cuda.device(dev):
-            packed = pack_state_dict(sd, self.model_type, self.n_mels, self.hidden_size, self.num_layers,
-                                     self.use_attention, self.use_onset_offset_heads, device=dev,
-                                     precise=self.precision == "precise")
             cfg = _lib.ModelConfig(1 if self._large() else 0, self.n_mels, self.hidden_size, self.num_layers, 8,
                                    int(self.use_attention), int(self.use_onset_offset_heads),
                                    int(self.precision == "precise"))
             handle = C.c_void_p()
             _lib.check(L.amt_model_create(C.byref(cfg), C.byref(handle)))
             try:
-                for name, t in packed.items():
-                    _lib.check(L.amt_model_set_tensor(handle, name.encode(), _lib.ptr(t), t.numel() * t.element_size()))
-                _lib.check(L.amt_model_finalize(handle))
+                n = len(sd)
+                names = (C.c_char_p * n)(*[k.encode() for k in sd])
+                ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in sd.values()])
+                numels = (C.c_int64 * n)(*[t.numel() for t in sd.values()])
+                _lib.check(L.amt_model_load(handle, names, ptrs, numels, n, _lib.stream_ptr(dev)))
             except Exception:
                 L.amt_model_destroy(handle)
                 raise
-        self._handle, self._packed, self._packed_key = handle, packed, key
+        self._handle, self._packed_key = handle, key
+
+    def packed_tensor(self, name: str, dtype) -> torch.Tensor:
+        """Copy of the packed tensor ``name`` the library built from the checkpoint (tests compare it with packing.py)."""
+        p, nbytes = C.c_void_p(), C.c_size_t()
+        _lib.check(_lib.lib().amt_model_get_tensor(self._handle, name.encode(), C.byref(p), C.byref(nbytes)))
+        dev = torch.device(self._packed_key[0])
+
+        class _Raw:          # zero-copy view of library-owned device memory through the CUDA array interface
+            __cuda_array_interface__ = {"shape": (nbytes.value,), "typestr": "|u1", "data": (p.value, True), "version": 2}
+        with torch.cuda.device(dev):
+            out = torch.as_tensor(_Raw(), device=dev).clone()
+        return out.view(dtype)
 
     def _release(self):
         if self._handle is not None:
             _lib.lib().amt_model_destroy(self._handle)
-        self._handle = self._packed = self._packed_key = None
+        self._handle = self._packed_key = None
 
     def __del__(self):
         try:
@@ -185,6 +208,12 @@ class TranscriptionModel(nn.Module):
         """x: (B, 1, n_mels, T) float32 CUDA -> logits (B, 88, T), or a dict with 'frame',
         'onset', 'offset' for the large model with heads when ``return_all_heads``
         (reference transcription_model.py:105-108, cnn_rnn_model.py:337-345)."""
+        if self.training and not self._warned_training:
+            import warnings
+            warnings.warn("TranscriptionModel (B200): forward always computes the EVAL-mode function (BatchNorm running statistics "
+                          "folded, dropout off, no autograd graph); call .eval() as reference main.py:52 does -- training is "
+                          "outside this implementation", stacklevel=2)
+            self._warned_training = True
         if x.dim() != 4 or x.shape[1] != 1 or x.shape[2] != self.n_mels:
             raise ValueError(f"expected input (B, 1, {self.n_mels}, T), got {tuple(x.shape)}")
         _lib.require_cuda(x, "TranscriptionModel input")

@@ -126,6 +126,48 @@ def test_model_matches_reference_golden(path):
     assert flips < 0.02
 
 
+@pytest.mark.parametrize("mt,n_mels,H,L,attn,heads", [
+    ("cnn_rnn_large", 64, 128, 2, True, True), ("cnn_rnn_large", 37, 128, 1, False, True), ("cnn_rnn_large", 64, 256, 1, True, False),
+    ("cnn_rnn", 64, 128, 2, True, True), ("cnn_rnn", 37, 256, 1, True, True)])
+@pytest.mark.parametrize("precision", ["fast", "precise"])
+def test_library_packing_is_bitwise_the_python_packing(mt, n_mels, H, L, attn, heads, precision):
+    """amt_model_load (CUDA kernels inside the library: BN fold in double, layouts, permutations, bf16 / split-bf16)
+    must produce exactly the tensors packing.pack_state_dict states in torch -- every packed tensor, bit for bit."""
+    from music_transcription_b200.packing import pack_state_dict
+    sd = synth.synth_state_dict(mt, n_mels, H, L, seed=9, use_attention=attn, use_onset_offset_heads=heads)
+    m = TranscriptionModel(mt, n_mels=n_mels, hidden_size=H, num_layers=L, device=DEV, use_attention=attn,
+                           use_onset_offset_heads=heads, precision=precision)
+    m.load_state_dict(sd, strict=True)
+    m(torch.zeros(1, 1, n_mels, 8, device=DEV))                       # packs
+    want = pack_state_dict(sd, mt, n_mels, H, L, attn, heads, precise=precision == "precise")
+    for name, t in want.items():
+        got = m.packed_tensor(name, t.dtype).cpu().view(t.shape)
+        assert torch.equal(got.view(torch.int16 if t.dtype == torch.bfloat16 else torch.int32),
+                           t.view(torch.int16 if t.dtype == torch.bfloat16 else torch.int32)), (name, (got.float() - t.float()).abs().max())
+
+
+def test_model_load_reports_missing_and_missized_tensors():
+    import ctypes as C
+    from music_transcription_b200 import _lib
+    L = _lib.lib()
+    cfg = _lib.ModelConfig(0, 64, 128, 1, 8, 1, 1, 0)
+    h = C.c_void_p()
+    _lib.check(L.amt_model_create(C.byref(cfg), C.byref(h)))
+    sd = {k: v.to(DEV).float().contiguous() for k, v in synth.synth_state_dict("cnn_rnn", 64, 128, 1, seed=1).items() if v.is_floating_point()}
+
+    def load(d):
+        n = len(d)
+        return L.amt_model_load(h, (C.c_char_p * n)(*[k.encode() for k in d]), (C.c_void_p * n)(*[t.data_ptr() for t in d.values()]),
+                                (C.c_int64 * n)(*[t.numel() for t in d.values()]), n, _lib.stream_ptr(torch.device(DEV)))
+    missing = {k: v for k, v in sd.items() if k != "model.fc.bias"}
+    assert load(missing) == _lib.AMT_ERR_STATE and b"model.fc.bias" in L.amt_last_error()
+    bad = dict(sd)
+    bad["model.cnn.4.weight"] = bad["model.cnn.4.weight"][:32].contiguous()
+    assert load(bad) == _lib.AMT_ERR_STATE and b"model.cnn.4.weight" in L.amt_last_error()
+    assert load(sd) == 0                                               # and the handle is usable after a failed attempt
+    L.amt_model_destroy(h)
+
+
 def test_stage_profile_and_in_flight_query():
     m = TranscriptionModel(model_type="cnn_rnn", n_mels=64, hidden_size=128, num_layers=1, device=DEV)
     m.load_state_dict(synth.synth_state_dict("cnn_rnn", 64, 128, 1, seed=3))
