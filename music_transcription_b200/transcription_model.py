@@ -179,7 +179,7 @@ class TranscriptionModel(nn.Module):
         dev = torch.device(self._packed_key[0])
 
         class _Raw:          # zero-copy view of library-owned device memory through the CUDA array interface
-            __cuda_array_interface__ = {"shape": (nbytes.value,), "typestr": "|u1", "data": (p.value, True), "version": 2}
+            __cuda_array_interface__ = {"shape": (nbytes.value,), "typestr": "|u1", "data": (p.value, False), "version": 2}
         with torch.cuda.device(dev):
             out = torch.as_tensor(_Raw(), device=dev).clone()
         return out.view(dtype)

@@ -359,3 +359,114 @@ def test_threshold_notes_takes_caller_scratch_and_rejects_a_short_one():
     st = L.amt_threshold_notes(_lib.ptr(p), 3, 88, 50, p.stride(0), p.stride(1), 0.5, _lib.ptr(notes), notes.shape[0],
                                _lib.ptr(counts), _lib.ptr(scratch), scratch.numel(), _stream())
     assert st == _lib.AMT_ERR_WORKSPACE and b"scratch" in L.amt_last_error()
+
+
+# ----------------------------------------------------------------------------- memory safety / determinism
+# compute-sanitizer is not available on this GPU pool (it answers "compute-sanitizer is closed on this pool"), so the
+# kernels' memory behaviour is checked directly: every output (and scratch) buffer sits between guard regions filled with a
+# sentinel, outputs are pre-filled with a second sentinel, each kernel runs twice, and the test asserts that (i) no guard
+# byte changed (no out-of-bounds write), (ii) every output element was written, (iii) both runs agree bit for bit (the
+# cross-CTA mbarrier / DSMEM protocols of the GEMM, conv, LSTM-cluster and attention kernels have no data race that
+# changes a result).  Shapes straddle tile boundaries (rows % 128 != 0, T % 64 != 0, odd F).
+GUARD = 4096
+
+
+class _Guarded:
+    def __init__(self, nbytes):
+        self.raw = torch.full((nbytes + 2 * GUARD,), 0xA5, dtype=torch.uint8, device=DEV)
+        self.body = self.raw[GUARD:GUARD + nbytes]
+        self.body.fill_(0xFF)                                    # bf16 / f32 NaN patterns: an unwritten element stays NaN
+
+    def view(self, dtype, *shape):
+        return self.body.view(dtype).view(*shape)
+
+    def intact(self):
+        return bool((self.raw[:GUARD] == 0xA5).all() and (self.raw[GUARD + self.body.numel():] == 0xA5).all())
+
+
+def _twice(run, outs):
+    res = []
+    for _ in range(2):
+        for o in outs:
+            o.body.fill_(0xFF)
+        run()
+        torch.cuda.synchronize()
+        res.append([o.body.clone() for o in outs])
+    for o, a, b in zip(outs, res[0], res[1]):
+        assert o.intact(), "guard region overwritten"
+        assert torch.equal(a, b), "two runs differ"
+    return res[0]
+
+
+def test_guarded_buffers_gemm_conv_attention():
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(0)
+    M, N, K = 333, 192, 320
+    a, w, b = _bf(torch.randn(M, K, generator=g)).to(DEV), _bf(torch.randn(N, K, generator=g)).to(DEV), torch.randn(N, generator=g).to(DEV)
+    for f32 in (0, 1):
+        out = _Guarded(M * N * (4 if f32 else 2))
+        _twice(lambda: _lib.check(L.amt_gemm_bf16(_lib.ptr(a), _lib.ptr(w), _lib.ptr(b), out.body.data_ptr(), M, N, K, N, 0, f32, _stream())), [out])
+        o = out.view(torch.float32 if f32 else torch.bfloat16, M, N).float()
+        assert torch.isfinite(o).all() and (o - (a.float() @ w.float().t() + b)).abs().max() < 0.5
+    for B, T, Fq, Ci, Co, kf, pool, split in ((2, 37, 21, 64, 128, 3, 1, 0), (1, 19, 11, 128, 256, 7, 0, 0), (1, 23, 10, 32, 64, 3, 1, 1)):
+        from music_transcription_b200.packing import split_act, split_k
+        x, wt = torch.randn(B, T, Fq, Ci, generator=g), torch.randn(Co, kf * 3 * Ci, generator=g) / (Ci * kf * 3) ** 0.5
+        xs, ws = (split_act(x, Ci), split_k(wt, Ci)) if split else (_bf(x), _bf(wt))
+        xs, ws, bias = xs.to(DEV).contiguous(), ws.to(DEV).contiguous(), torch.randn(Co, generator=g).to(DEV)
+        Fo = Fq // 2 if pool else Fq
+        out = _Guarded(B * T * Fo * Co * (3 if split else 1) * 2)
+        _twice(lambda: _lib.check(L.amt_conv_bf16(_lib.ptr(xs), 0, _lib.ptr(ws), _lib.ptr(bias), out.body.data_ptr(), B, T, Fq, xs.shape[-1], 0,
+                                                  Co, kf, 3, 1, pool | (2 if split else 0), _stream())), [out])
+        assert torch.isfinite(out.view(torch.bfloat16, -1).float()).all()
+    for B, T, hd in ((2, 150, 192), (1, 70, 64), (1, 70, 48)):
+        D = 8 * hd
+        qkv = _bf(torch.randn(B * T, 3 * D, generator=g)).to(DEV)
+        out = _Guarded(B * T * D * 2)
+        _twice(lambda: _lib.check(L.amt_attention_bf16(_lib.ptr(qkv), out.body.data_ptr(), B, T, 8, hd, 10.0, _stream())), [out])
+        assert torch.isfinite(out.view(torch.bfloat16, -1).float()).all()
+
+
+def test_guarded_buffers_lstm_cluster_and_fallback():
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(1)
+    for B, T, Hs in ((5, 9, (512, 512, 256, 256)), (37, 7, (128, 128)), (3, 5, (640, 640))):
+        seqs = (_lib.LstmSeq * len(Hs))()
+        keep, outs = [], []
+        for i, H in enumerate(Hs):
+            whh = _bf(torch.randn(4 * H, H, generator=g) / H ** 0.5)[slice_order(H)].contiguous().to(DEV)
+            gx = torch.randn(B * T, 4 * H, generator=g).to(DEV)
+            ob, of = _Guarded(B * T * H * 2), _Guarded(B * T * H * 4)
+            keep += [whh, gx]
+            outs += [ob, of]
+            seqs[i] = _lib.LstmSeq(_lib.ptr(whh), _lib.ptr(gx), ob.body.data_ptr(), of.body.data_ptr(), H, i & 1, 4 * H, H, H)
+        nb = L.amt_lstm_scratch_bytes(seqs, len(Hs), B)
+        scratch = _Guarded(nb)
+        scratch.body.zero_()
+        res = _twice(lambda: _lib.check(L.amt_lstm_recurrence(seqs, len(Hs), B, T, scratch.body.data_ptr(), nb, _stream())), outs)
+        assert scratch.intact()
+        for r in res[1::2]:
+            assert torch.isfinite(r.view(torch.float32)).all() and r.view(torch.float32).abs().max() <= 1.0
+
+
+def test_guarded_buffers_frontend_notes_pack():
+    from music_transcription_b200 import pipeline
+    L = _lib.lib()
+    fe = pipeline.Frontend.get(device=DEV)
+    n = 3 * 512 + 77                                             # T = 4 frames, ragged tail
+    wav = torch.from_numpy(synth.piano_chord_batch([0, 1], n_samples=n)).to(DEV)
+    out, cmax = _Guarded(2 * 320 * 4 * 4), _Guarded(2 * 4)
+    _twice(lambda: _lib.check(L.amt_logmel_f32(fe._h, _lib.ptr(wav), 2, n, n, out.body.data_ptr(), 80.0, cmax.body.data_ptr(), _stream())), [out, cmax])
+    assert torch.isfinite(out.view(torch.float32, -1)).all()
+    T, n_seg = 70, 3
+    p = torch.rand(n_seg, 88, T, device=DEV)
+    cap = 88 * ((n_seg * T + 1) // 2)
+    notes, counts, scratch, bits = _Guarded(cap * 12), _Guarded(89 * 4), _Guarded(2 * 88 * n_seg * 4), _Guarded(n_seg * 88 * 3 * 4)
+
+    def run():
+        _lib.check(L.amt_threshold_notes(_lib.ptr(p), n_seg, 88, T, p.stride(0), p.stride(1), 0.5, notes.body.data_ptr(), cap,
+                                         counts.body.data_ptr(), scratch.body.data_ptr(), 2 * 88 * n_seg, _stream()))
+        _lib.check(L.amt_pack_roll_u32(_lib.ptr(p), n_seg * 88, T, 0.5, 0, bits.body.data_ptr(), _stream()))
+    res = _twice(run, [counts, bits])
+    assert notes.intact() and scratch.intact()
+    total = int(res[0].view(torch.int32)[88])
+    assert 0 < total <= cap
