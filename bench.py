@@ -323,6 +323,7 @@ def main():
     fe = pipeline.Frontend.get(device=dev)
     cap = 88 * ((n_local * T + 1) // 2)
     probs = torch.empty(n_local, 88, T, device=dev)
+    rolls = torch.empty(n_local, 88, (T + 31) // 32, dtype=torch.int32, device=dev)
     notes = torch.empty(cap, 3, dtype=torch.int32, device=dev)
     counts = torch.empty(89, dtype=torch.int32, device=dev)
     scratch = torch.empty(2 * 88 * n_local, dtype=torch.int32, device=dev)
@@ -332,9 +333,11 @@ def main():
         for a, b in batches:
             mel = fe.logmel(wav[a:b])
             logits = model(mel)
-            _lib.check(L.amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), 0.5, _lib.ptr(probs[a:b]), 0, stream))
-        pipeline.extract_notes_async(probs, 0.5, notes, counts, scratch)       # seams between this rank's chunks merge here
-        result["notes"] = sharding.gather_notes_device(notes, counts, lo * T)  # -> host, stitched across ranks
+            # sigmoid + strict float32 '>' (main.py:153-156), straight into the bit-packed roll (10.6 KB per chunk)
+            _lib.check(L.amt_pack_roll_u32(_lib.ptr(logits), (b - a) * 88, T, 0.5, 1, _lib.ptr(rolls[a:b]), stream))
+        # the one exchange of the path: all-gather the packed rolls over NCCL / NVLink, group the gathered roll once on
+        # the GPU (seams between chunks, batches and ranks merge in the kernel), note list -> host on every rank
+        result["notes"] = sharding.gather_rolls_notes(rolls, T, R)
 
     # End to end through the public API with HOST buffers: pipeline.StreamingTranscriber copies batch i+1 in and batch i-1
     # out while batch i computes; every batch still moves its own audio in and its rolls + notes out.

@@ -175,6 +175,12 @@ int amt_threshold_notes(const float* vals, int n_seg, int n_pitch, int T, int64_
                         int64_t pitch_stride, float thr, int32_t* notes, int cap, int32_t* counts,
                         int32_t* scratch, size_t scratch_ints, amt_stream_t stream);
 
+/* The same grouping on BIT-PACKED rolls (amt_pack_roll_u32): bits [n_seg][n_pitch][ceil(T/32)], segments concatenated
+ * along time.  This is the form in which rolls cross NVLink: every rank all-gathers its chunks' packed rolls (10.6 KB per
+ * chunk) and ONE grouping pass over the gathered roll yields the recording's note list, seams included. */
+int amt_bits_notes(const uint32_t* bits, int n_seg, int n_pitch, int T, int32_t* notes, int cap, int32_t* counts,
+                   int32_t* scratch, size_t scratch_ints, amt_stream_t stream);
+
 /* Framewise TP/FP/FN of reference scripts/evaluate.py:524-553 for every piece
  * and every threshold in one pass.  probs/target: [n_pieces][n_pitch][T_stride]
  * f32, only the first lengths[i] frames of piece i count; thresholds: sorted

@@ -16,8 +16,9 @@ namespace amt {
 // per-warp onset / offset counts into output ranks, so the note list comes out pitch-major and
 // onset-ascending exactly as the reference loop emits it (main.py:204-223).
 struct RollView {
-  const float* vals;
-  int n_seg, T;
+  const float* vals;          // float roll / probabilities, or nullptr when `bits` is set
+  const uint32_t* bits;       // bit-packed roll [n_seg][n_pitch][words]: bit t%32 of word t/32 (amt_pack_roll_u32)
+  int n_seg, T, words, n_pitch;
   long long seg_stride, pitch_stride;
   float thr;
   // frame t of segment s, where t may be -1 (last frame of the previous segment) or T (first of the next)
@@ -25,6 +26,7 @@ struct RollView {
     if (t < 0) { --s; t = T - 1; }
     else if (t >= T) { ++s; t = 0; }
     if (s < 0 || s >= n_seg) return false;
+    if (bits) return (__ldg(bits + (static_cast<long long>(s) * n_pitch + p) * words + (t >> 5)) >> (t & 31)) & 1u;
     return __ldg(vals + s * seg_stride + p * pitch_stride + t) > thr;
   }
 };
@@ -178,18 +180,12 @@ size_t amt_threshold_notes_scratch_ints(int n_seg, int n_pitch) {
   return 2 * static_cast<size_t>(n_seg) * static_cast<size_t>(n_pitch);
 }
 
-int amt_threshold_notes(const float* vals, int n_seg, int n_pitch, int T, int64_t seg_stride, int64_t pitch_stride,
-                        float thr, int32_t* notes, int cap, int32_t* counts, int32_t* scratch, size_t scratch_ints,
-                        amt_stream_t stream_) {
+static int group_notes(amt::RollView rv, int n_pitch, int32_t* notes, int cap, int32_t* counts, int32_t* scratch,
+                       size_t scratch_ints, cudaStream_t stream) {
   using namespace amt;
-  AMT_REQUIRE(vals && notes && counts && scratch, "threshold_notes: NULL argument");
-  AMT_REQUIRE(n_seg >= 1 && n_pitch >= 1 && T >= 1 && cap >= 0, "threshold_notes: bad sizes");
-  AMT_TRY(ensure_device());
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   AMT_REQUIRE(n_pitch <= 1024, "threshold_notes: at most 1024 pitches");
-  AMT_REQUIRE(static_cast<long long>(n_seg) * T < (1ll << 31), "threshold_notes: roll too long");
-  RollView rv{vals, n_seg, T, seg_stride, pitch_stride, thr};
-  const int n = n_pitch * n_seg;
+  AMT_REQUIRE(static_cast<long long>(rv.n_seg) * rv.T < (1ll << 31), "threshold_notes: roll too long");
+  const int n = n_pitch * rv.n_seg;
   // per-(pitch, segment) onset / offset counts -> ranks, in CALLER scratch (the library owns no device memory:
   // nothing here is tied to one device, one stream or one host thread, and the call is graph-capturable)
   if (scratch_ints < 2 * static_cast<size_t>(n))
@@ -198,11 +194,32 @@ int amt_threshold_notes(const float* vals, int n_seg, int n_pitch, int T, int64_
   const int grid = ceil_div(n, 8);
   notes_scan_kernel<false><<<grid, 256, 0, stream>>>(rv, n_pitch, scratch, scratch + n, notes, cap);
   AMT_CHECK_LAUNCH();
-  notes_rank_kernel<<<1, 1024, 0, stream>>>(scratch, scratch + n, n, n_seg, n_pitch, counts);
+  notes_rank_kernel<<<1, 1024, 0, stream>>>(scratch, scratch + n, n, rv.n_seg, n_pitch, counts);
   AMT_CHECK_LAUNCH();
   notes_scan_kernel<true><<<grid, 256, 0, stream>>>(rv, n_pitch, scratch, scratch + n, notes, cap);
   AMT_CHECK_LAUNCH();
   return 0;
+}
+
+int amt_threshold_notes(const float* vals, int n_seg, int n_pitch, int T, int64_t seg_stride, int64_t pitch_stride,
+                        float thr, int32_t* notes, int cap, int32_t* counts, int32_t* scratch, size_t scratch_ints,
+                        amt_stream_t stream_) {
+  using namespace amt;
+  AMT_REQUIRE(vals && notes && counts && scratch, "threshold_notes: NULL argument");
+  AMT_REQUIRE(n_seg >= 1 && n_pitch >= 1 && T >= 1 && cap >= 0, "threshold_notes: bad sizes");
+  AMT_TRY(ensure_device());
+  RollView rv{vals, nullptr, n_seg, T, 0, n_pitch, seg_stride, pitch_stride, thr};
+  return group_notes(rv, n_pitch, notes, cap, counts, scratch, scratch_ints, static_cast<cudaStream_t>(stream_));
+}
+
+int amt_bits_notes(const uint32_t* bits, int n_seg, int n_pitch, int T, int32_t* notes, int cap, int32_t* counts,
+                   int32_t* scratch, size_t scratch_ints, amt_stream_t stream_) {
+  using namespace amt;
+  AMT_REQUIRE(bits && notes && counts && scratch, "bits_notes: NULL argument");
+  AMT_REQUIRE(n_seg >= 1 && n_pitch >= 1 && T >= 1 && cap >= 0, "bits_notes: bad sizes");
+  AMT_TRY(ensure_device());
+  RollView rv{nullptr, bits, n_seg, T, (T + 31) / 32, n_pitch, 0, 0, 0.0f};
+  return group_notes(rv, n_pitch, notes, cap, counts, scratch, scratch_ints, static_cast<cudaStream_t>(stream_));
 }
 
 int amt_f1_counts(const float* probs, const float* target, const int32_t* lengths, int n_pieces, int n_pitch,

@@ -192,6 +192,31 @@ def extract_notes_async(vals: torch.Tensor, threshold: float, notes_out: torch.T
                                                   _lib.stream_ptr(vals.device)))
 
 
+def extract_notes_from_bits(bits: torch.Tensor, T: int, cap: int | None = None) -> np.ndarray:
+    """``extract_notes`` on bit-packed rolls (``pack_roll``): bits int32 (n_seg, 88, ceil(T/32)) CUDA, the segments
+    concatenated along time.  Same output as grouping the float roll the bits came from."""
+    _lib.require_cuda(bits, "extract_notes_from_bits input")
+    if bits.dim() == 2:
+        bits = bits[None]
+    bits = bits.contiguous()
+    n_seg, n_pitch, words = bits.shape
+    if words != (T + 31) // 32:
+        raise ValueError(f"extract_notes_from_bits: {words} words per row do not hold T = {T} frames")
+    dev = bits.device
+    if cap is None:
+        cap = n_pitch * ((n_seg * T + 1) // 2)
+    notes = torch.empty(max(cap, 1), 3, dtype=torch.int32, device=dev)
+    counts = torch.empty(n_pitch + 1, dtype=torch.int32, device=dev)
+    scratch = torch.empty(2 * n_seg * n_pitch, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().amt_bits_notes(_lib.ptr(bits), n_seg, n_pitch, T, _lib.ptr(notes), cap, _lib.ptr(counts),
+                                             _lib.ptr(scratch), scratch.numel(), _lib.stream_ptr(dev)))
+    total = int(counts[n_pitch].item())
+    if total > cap:
+        raise _lib.AmtError(f"extract_notes_from_bits: {total} notes exceed cap {cap}")
+    return notes[:total].cpu().numpy()
+
+
 def pianoroll_to_midi(pianoroll, fs, min_midi=21) -> NoteList:
     """(88, T) roll (numpy or tensor, values {0,1}) -> notes, grouped on the GPU (main.py:204-223)."""
     roll = torch.as_tensor(np.ascontiguousarray(pianoroll, dtype=np.float32)) if not torch.is_tensor(pianoroll) else pianoroll

@@ -14,6 +14,7 @@ small gather at the end (NCCL over NVLink on GPUs, gloo in the CPU tests):
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Tuple
 
 import numpy as np
@@ -29,50 +30,72 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _merge_at(notes: np.ndarray, idx: np.ndarray) -> np.ndarray:
+    """Rows ``idx`` (sorted) continue the row before them: drop them and hand their offset to the surviving row."""
+    if len(idx) == 0:
+        return notes
+    run_end = np.append(np.diff(idx) != 1, True)              # last row of each run of consecutive merged rows
+    run_start = np.append(True, run_end[:-1])
+    out = notes.copy()
+    out[idx[run_start] - 1, 2] = notes[idx[run_end], 2]
+    return np.delete(out, idx, axis=0)
+
+
 def merge_touching(notes: np.ndarray) -> np.ndarray:
     """notes int (n,3) sorted by (pitch, onset): merge runs of consecutive rows of one pitch whose offset == the next
     onset (a note cut by one or more shard seams).  Vectorised: a 2-hour recording has ~10^5 notes."""
     notes = np.asarray(notes).reshape(-1, 3)
-    n = len(notes)
-    if n == 0:
+    if len(notes) < 2:
         return notes
-    cont = np.zeros(n, dtype=bool)                       # row i continues row i-1
-    cont[1:] = (notes[1:, 0] == notes[:-1, 0]) & (notes[1:, 1] == notes[:-1, 2])
-    starts = np.flatnonzero(~cont)
-    last = np.append(starts[1:], n) - 1
-    out = notes[starts].copy()
-    out[:, 2] = notes[last, 2]
-    return out
+    cont = (notes[1:, 0] == notes[:-1, 0]) & (notes[1:, 1] == notes[:-1, 2])        # row i+1 continues row i
+    return _merge_at(notes, np.flatnonzero(cont) + 1)
 
 
 def stitch_notes(per_rank, per_pitch_counts=None) -> np.ndarray:
     """per_rank: list (rank / batch order = time order) of int32 (n_r,3) note arrays with GLOBAL frame indices, each
-    pitch-major / onset-ascending.  Returns the note list of the concatenated roll.  With ``per_pitch_counts``
-    (list of int arrays: notes per pitch in each part, as amt_threshold_notes reports them) the pitch-major merge is
-    done by slicing; without, by a stable sort."""
+    pitch-major / onset-ascending.  Returns the note list of the concatenated roll: the parts are interleaved pitch by
+    pitch (slices located by the per-pitch note counts -- ``per_pitch_counts`` as amt_threshold_notes reports them, else
+    recounted here) and only the rows at part boundaries, the one place a cut note can sit, are tested for merging."""
     per_rank = [np.asarray(a, dtype=np.int32).reshape(-1, 3) for a in per_rank]
     if not per_rank or sum(len(a) for a in per_rank) == 0:
         return np.zeros((0, 3), np.int32)
     if len(per_rank) == 1:
         return merge_touching(per_rank[0])
-    if per_pitch_counts is not None:
-        offs = [np.concatenate([[0], np.cumsum(np.asarray(c, dtype=np.int64))]) for c in per_pitch_counts]
-        n_pitch = len(offs[0]) - 1
-        pieces = [a[o[p]:o[p + 1]] for p in range(n_pitch) for a, o in zip(per_rank, offs)]
-        allnotes = np.concatenate(pieces, axis=0)
-    else:
-        allnotes = np.concatenate(per_rank, axis=0)
-        order = np.lexsort((allnotes[:, 1], allnotes[:, 0]))    # by pitch, then onset (parts are time-ordered)
-        allnotes = allnotes[order]
-    return merge_touching(allnotes)
+    if per_pitch_counts is None:
+        n_pitch = max(int(a[:, 0].max()) + 1 for a in per_rank if len(a))
+        per_pitch_counts = [np.bincount(a[:, 0], minlength=n_pitch) for a in per_rank]
+    c = np.stack([np.asarray(x, dtype=np.int64) for x in per_pitch_counts])        # [parts][pitches]
+    offs = np.concatenate([np.zeros((len(c), 1), np.int64), np.cumsum(c, axis=1)], axis=1)
+    n_pitch = c.shape[1]
+    allnotes = np.concatenate([a[o[p]:o[p + 1]] for p in range(n_pitch) for a, o in zip(per_rank, offs)], axis=0)
+    seg = c.T.reshape(-1)                                                           # segment sizes in (pitch, part) order
+    start = np.cumsum(seg) - seg
+    part = np.tile(np.arange(len(c)), n_pitch)
+    cand = start[(seg > 0) & (part > 0) & (start > 0)]                              # first row of every later part's segment
+    cand = cand[(allnotes[cand, 0] == allnotes[cand - 1, 0]) & (allnotes[cand, 1] == allnotes[cand - 1, 2])]
+    return _merge_at(allnotes, cand)
 
 
 def _device_for_backend():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
 
+_SIDE = {}
+
+
+def _side_stream(dev):
+    """Collectives whose inputs come from the HOST have no business waiting behind whatever compute the caller has
+    already queued on its stream (NCCL orders itself after the *current* stream): they run under a side stream."""
+    if dev.type != "cuda":
+        return None
+    key = str(dev)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(dev)
+    return _SIDE[key]
+
+
 def gather_notes(local_notes: np.ndarray, frame_offset: int) -> np.ndarray:
-    """All ranks call this with their local note list (frame indices local to their block) and the
+    """All ranks call this with their local note list (host array, frame indices local to their block) and the
     global frame index of their first frame.  Every rank returns the stitched global list."""
     local = np.asarray(local_notes, dtype=np.int32).reshape(-1, 3).copy()
     local[:, 1:] += np.int32(frame_offset)
@@ -80,17 +103,29 @@ def gather_notes(local_notes: np.ndarray, frame_offset: int) -> np.ndarray:
         return merge_touching(local)
     dev = _device_for_backend()
     world = dist.get_world_size()
-    n = torch.tensor([len(local)], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n)
-    counts = [int(c.item()) for c in counts]
-    cap = max(max(counts), 1)
-    buf = torch.zeros(cap, 3, dtype=torch.int32, device=dev)
-    if len(local):
-        buf[:len(local)] = torch.from_numpy(local).to(dev)
-    bufs = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(bufs, buf)
-    return stitch_notes([b[:c].cpu().numpy() for b, c in zip(bufs, counts)])
+    n_pitch = 88 if not len(local) else max(88, int(local[:, 0].max()) + 1)
+    side = _side_stream(dev)
+    ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+    with ctx:
+        # per-pitch counts travel with the lists: the merge on the host is then a slice interleave, not a sort
+        head = torch.zeros(1 + 1024, dtype=torch.int64)
+        head[0] = len(local)
+        head[1:1 + n_pitch] = torch.from_numpy(np.bincount(local[:, 0], minlength=n_pitch).astype(np.int64))
+        head = head.to(dev)
+        heads = [torch.zeros_like(head) for _ in range(world)]
+        dist.all_gather(heads, head)
+        heads = torch.stack(heads).cpu().numpy()
+        counts = [int(h[0]) for h in heads]
+        cap = max(max(counts), 1)
+        buf = torch.zeros(cap, 3, dtype=torch.int32)
+        if len(local):
+            buf[:len(local)] = torch.from_numpy(local)
+        buf = buf.to(dev)
+        bufs = [torch.zeros_like(buf) for _ in range(world)]
+        dist.all_gather(bufs, buf)
+        parts = [b[:c].cpu().numpy() for b, c in zip(bufs, counts)]
+    n_pitch = int(max(np.flatnonzero(heads[:, 1:].sum(0) > 0).max(initial=0) + 1, 1))
+    return stitch_notes(parts, [h[1:1 + n_pitch] for h in heads])
 
 
 def gather_notes_device(notes_dev: torch.Tensor, counts_dev: torch.Tensor, frame_offset: int) -> np.ndarray:
@@ -118,6 +153,28 @@ def gather_notes_device(notes_dev: torch.Tensor, counts_dev: torch.Tensor, frame
     dist.all_gather_into_tensor(allb, send)
     allb = allb.cpu().numpy()
     return stitch_notes([allb[r, :totals[r]] for r in range(world)], [allc[r, :n_pitch] for r in range(world)])
+
+
+def gather_rolls_notes(bits_local: torch.Tensor, T: int, n_total: int) -> np.ndarray:
+    """The N > 1 exchange of DESIGN.md section 6 in its roll form: ``bits_local`` int32
+    (n_local, 88, ceil(T/32)) CUDA = this rank's bit-packed rolls (its ``shard_range`` of the ``n_total`` chunks).
+    ONE all-gather of 10.6 KB per chunk over NCCL / NVLink, then one grouping pass over the gathered roll on the GPU
+    (``amt_bits_notes``): the note list of the whole recording, seams included, with no host-side merging.  Every rank
+    returns it.  Single process: just the grouping pass."""
+    from . import pipeline
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        return pipeline.extract_notes_from_bits(bits_local, T)
+    n_pitch, words = bits_local.shape[1], bits_local.shape[2]
+    sizes = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
+    cap = max(sizes)
+    send = bits_local.contiguous()
+    if send.shape[0] < cap:                                                       # uneven shards: pad the short ones
+        send = torch.cat([send, torch.zeros(cap - send.shape[0], n_pitch, words, dtype=send.dtype, device=send.device)])
+    allb = torch.empty(world, cap, n_pitch, words, dtype=send.dtype, device=send.device)
+    dist.all_gather_into_tensor(allb, send)
+    rolls = allb.view(world * cap, n_pitch, words) if min(sizes) == cap else torch.cat([allb[r, :sizes[r]] for r in range(world)])
+    return pipeline.extract_notes_from_bits(rolls, T)
 
 
 def gather_counts(local_counts, n_total: int) -> np.ndarray:

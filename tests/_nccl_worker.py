@@ -40,7 +40,9 @@ def main():
     got = sharding.gather_notes_device(notes, counts, lo * T)
     local_np = notes[:int(counts[88])].cpu().numpy()
     got_np = sharding.gather_notes(local_np, lo * T)               # the numpy-input variant (gloo-tested on CPU) over NCCL
+    got_rolls = sharding.gather_rolls_notes(pipeline.pack_roll(probs, 0.5), T, n)   # the roll form: bits all-gathered, one grouping pass
     want, _ = pipeline.transcribe_chunks(m, wav_all.to(dev), threshold=0.5, batch=64)
+    assert np.array_equal(got_rolls, want), (rank, len(got_rolls), len(want))
     assert len(want) > 50, len(want)
     assert np.array_equal(got, want), (rank, len(got), len(want))
     assert np.array_equal(got_np, want)

@@ -349,6 +349,24 @@ def test_pack_roll_bits_equal_float_roll():
         assert np.array_equal(pipeline.unpack_roll(pipeline.pack_roll(logits, 0.5, apply_sigmoid=True), T), roll.cpu().numpy())
 
 
+def test_bits_notes_equals_float_notes_incl_seams():
+    """amt_bits_notes on the bit-packed roll == amt_threshold_notes on the probabilities it was packed from, for a
+    multi-segment roll with notes crossing the seams and T not a multiple of 32."""
+    from music_transcription_b200 import pipeline
+    from oracle import notes as onotes
+    for n_seg, T in ((5, 938), (3, 33), (1, 64)):
+        p = torch.from_numpy(np.stack([synth.planted_probs(88, T, [0.5], seed=10 * n_seg + i, frac=0.05) for i in range(n_seg)])).to(DEV)
+        p[:, 10, :] = 0.9                                         # sounds through every seam
+        if n_seg > 1:
+            p[0, 20, T - 2:] = 0.9
+            p[1, 20, :3] = 0.9
+        want = pipeline.extract_notes(p, 0.5)
+        got = pipeline.extract_notes_from_bits(pipeline.pack_roll(p, 0.5), T)
+        assert np.array_equal(got, want)
+        roll = np.concatenate([onotes.threshold_roll(x, 0.5) for x in p.cpu().numpy()], axis=1)
+        assert np.array_equal(got, onotes.group_notes(roll))
+
+
 def test_threshold_notes_takes_caller_scratch_and_rejects_a_short_one():
     L = _lib.lib()
     assert L.amt_threshold_notes_scratch_ints(3, 88) == 2 * 3 * 88
