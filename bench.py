@@ -344,20 +344,27 @@ def main():
     streamer = pipeline.StreamingTranscriber(model, B0, N_SAMPLES, 0.5, input_format="pcm16", roll_format="bits")
     e2e_stats = {"d2h": 0}
 
+    rec_bits = torch.zeros(n_local, 88, (T + 31) // 32, dtype=torch.int32)        # this rank's packed rolls of one recording (host)
+    gatherer = sharding.AsyncRollGather(n_local, R, T, dev)
+
     def run_e2e(steps):
+        """Batch after batch through the streamer; when a recording's last batch has arrived on the host, its packed rolls go
+        to the asynchronous roll exchange (upload 10.6 KB per chunk, all-gather, one grouping pass, note list back) on a side
+        stream, and the PREVIOUS recording's note list is collected -- the host never waits behind queued batches."""
         feed = (pcm_host[a:b] for _ in range(steps) for a, b in batches)
-        acc, per_pitch, d2h = [], [], 0
+        d2h, pending = 0, None
         for i, (roll, nts) in enumerate(streamer.run(feed)):
-            a = batches[i % len(batches)][0]
-            g = nts.copy()
-            g[:, 1:] += (lo + a) * T
-            acc.append(g)
-            per_pitch.append(np.bincount(g[:, 0], minlength=88))
-            d2h += roll.numel() * 4 + 89 * 4 + nts.size * 4
-            if i % len(batches) == len(batches) - 1:                            # the recording's last batch on this rank
-                local = sharding.stitch_notes(acc, per_pitch)                   # host work, hidden behind the next batch's compute
-                acc, per_pitch = [], []
-                result["e2e_notes"] = sharding.gather_notes(local, 0) if world > 1 else local
+            a, b = batches[i % len(batches)]
+            rec_bits[a:b].copy_(roll)
+            d2h += roll.numel() * 4 + 89 * 4 + nts.size * 4                      # what the streamer downloaded for this batch
+            if i % len(batches) == len(batches) - 1:                              # the recording's last batch on this rank
+                ticket = gatherer.submit(rec_bits)
+                if pending is not None:
+                    result["e2e_notes"] = gatherer.result(pending)
+                pending = ticket
+        if pending is not None:
+            result["e2e_notes"] = gatherer.result(pending)
+            d2h += (result["e2e_notes"].size + 89) * 4 * steps                    # the recording's note list, once per step
         e2e_stats["d2h"] = d2h // max(steps, 1)
 
     def barrier():
@@ -398,7 +405,7 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     ms_e2e = float(t_e2e.item())
     e2e_value = R * args.steps / (ms_e2e / 1e3)
-    io = torch.tensor([n_local * N_SAMPLES * 2, e2e_stats["d2h"]], dtype=torch.int64, device=dev)
+    io = torch.tensor([n_local * N_SAMPLES * 2 + rec_bits.numel() * 4, e2e_stats["d2h"]], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(io)                                                      # whole-job bytes per step (all ranks)
     h2d, d2h = int(io[0].item()), int(io[1].item())
@@ -508,8 +515,9 @@ def main():
                 "config": workload_config(args, world, n_local, batches),
                 "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": round(ms_e2e / args.steps, 3), "sm_mhz": clocks_e2e["sm_mhz"],
-                        "api": "pipeline.StreamingTranscriber(input_format='pcm16', roll_format='bits') + sharding.stitch_notes / "
-                               "gather_notes; bytes are whole-job totals per step (all ranks)",
+                        "api": "pipeline.StreamingTranscriber(input_format='pcm16', roll_format='bits') per batch + "
+                               "sharding.AsyncRollGather per recording (packed rolls all-gathered, one grouping pass, note list to the "
+                               "host of every rank, one recording behind the compute); bytes are whole-job totals per step (all ranks)",
                         "notes_equal_device_path": same},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "model_tflops_whole_step": round(total_flops * args.steps / (ms / 1e3) / 1e12, 2),

@@ -177,6 +177,91 @@ def gather_rolls_notes(bits_local: torch.Tensor, T: int, n_total: int) -> np.nda
     return pipeline.extract_notes_from_bits(rolls, T)
 
 
+class AsyncRollGather:
+    """``gather_rolls_notes`` for a STREAMING host: the packed rolls of a finished recording are handed over from pinned
+    host memory (where the streaming path has just delivered them), and upload, all-gather, grouping pass and download of
+    the note list all run on a side stream while the caller's stream is already busy with the next recording.  The host
+    never waits for work queued behind future batches: ``submit`` returns at once, ``result`` is asked for one recording
+    later (two slots).
+
+        g = AsyncRollGather(n_local, n_total, T, device)
+        t = g.submit(bits_host)        # int32 (n_local, 88, ceil(T/32)) host tensor / array
+        ...                            # launch the next recording's batches
+        notes = g.result(t)            # int32 (n, 3) numpy: the whole recording's note list
+    """
+
+    ROWS_PER_CHUNK = 1024              # rows of the note list downloaded blindly; more -> one extra blocking copy
+
+    def __init__(self, n_local: int, n_total: int, T: int, device, n_pitch: int = 88):
+        self.n_local, self.n_total, self.T, self.n_pitch = n_local, n_total, T, n_pitch
+        self.dev = torch.device(device)
+        self.words = (T + 31) // 32
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.sizes = [shard_range(n_total, r, self.world)[1] - shard_range(n_total, r, self.world)[0] for r in range(self.world)]
+        if self.sizes[self.rank] != n_local:
+            raise ValueError("AsyncRollGather: n_local is not this rank's shard_range of n_total")
+        self.side = torch.cuda.Stream(self.dev)
+        cap_chunks = max(self.sizes)
+        self.cap = n_pitch * ((n_total * T + 1) // 2)
+        self.guess = min(self.cap, self.ROWS_PER_CHUNK * n_total)
+        self.slots = []
+        for _ in range(2):
+            sl = {"host_bits": torch.zeros(cap_chunks, n_pitch, self.words, dtype=torch.int32).pin_memory(),
+                  "bits": torch.zeros(cap_chunks, n_pitch, self.words, dtype=torch.int32, device=self.dev),
+                  "all": torch.empty(self.world, cap_chunks, n_pitch, self.words, dtype=torch.int32, device=self.dev),
+                  "notes": torch.empty(self.cap, 3, dtype=torch.int32, device=self.dev),
+                  "counts": torch.empty(n_pitch + 1, dtype=torch.int32, device=self.dev),
+                  "scratch": torch.empty(2 * n_pitch * n_total, dtype=torch.int32, device=self.dev),
+                  "host_notes": torch.empty(self.guess, 3, dtype=torch.int32).pin_memory(),
+                  "host_counts": torch.zeros(n_pitch + 1, dtype=torch.int32).pin_memory(),
+                  "done": torch.cuda.Event(), "busy": False}
+            self.slots.append(sl)
+        self.n = 0
+
+    def submit(self, bits_host) -> int:
+        from . import _lib
+        ticket = self.n
+        sl = self.slots[ticket & 1]
+        if sl["busy"]:
+            raise RuntimeError("AsyncRollGather: collect result(ticket - 2) before submitting again")
+        src = bits_host if torch.is_tensor(bits_host) else torch.from_numpy(np.ascontiguousarray(bits_host))
+        sl["host_bits"][:self.n_local].copy_(src.view(torch.int32).reshape(self.n_local, self.n_pitch, self.words))
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.side):
+            sl["bits"].copy_(sl["host_bits"], non_blocking=True)
+            if self.world > 1:
+                dist.all_gather_into_tensor(sl["all"], sl["bits"])
+                cap = sl["all"].shape[1]
+                rolls = (sl["all"].view(self.world * cap, self.n_pitch, self.words) if min(self.sizes) == cap
+                         else torch.cat([sl["all"][r, :self.sizes[r]] for r in range(self.world)]))
+            else:
+                rolls = sl["bits"][:self.n_local]
+            _lib.check(_lib.lib().amt_bits_notes(_lib.ptr(rolls), self.n_total, self.n_pitch, self.T, _lib.ptr(sl["notes"]), self.cap,
+                                                 _lib.ptr(sl["counts"]), _lib.ptr(sl["scratch"]), sl["scratch"].numel(),
+                                                 self.side.cuda_stream))
+            sl["host_counts"].copy_(sl["counts"], non_blocking=True)
+            sl["host_notes"].copy_(sl["notes"][:self.guess], non_blocking=True)
+            sl["done"].record(self.side)
+            sl["rolls_keepalive"] = rolls
+        sl["busy"] = True
+        self.n += 1
+        return ticket
+
+    def result(self, ticket: int) -> np.ndarray:
+        sl = self.slots[ticket & 1]
+        if not sl["busy"]:
+            raise RuntimeError("AsyncRollGather: no submission pending in this slot")
+        sl["done"].synchronize()
+        total = int(sl["host_counts"][self.n_pitch])
+        if total <= self.guess:
+            out = sl["host_notes"][:total].numpy().copy()
+        else:                                                      # denser than ROWS_PER_CHUNK notes per chunk: fetch the rest
+            with torch.cuda.device(self.dev), torch.cuda.stream(self.side):
+                out = sl["notes"][:total].cpu().numpy()
+        sl["busy"] = False
+        return out
+
+
 def gather_counts(local_counts, n_total: int) -> np.ndarray:
     """local_counts int64 [n_local, n_thr, 3] (numpy, or a tensor on the backend's device) for this rank's
     ``shard_range`` of ``n_total`` pieces -> int64 [n_total, n_thr, 3] on every rank."""

@@ -43,6 +43,18 @@ def main():
     got_rolls = sharding.gather_rolls_notes(pipeline.pack_roll(probs, 0.5), T, n)   # the roll form: bits all-gathered, one grouping pass
     want, _ = pipeline.transcribe_chunks(m, wav_all.to(dev), threshold=0.5, batch=64)
     assert np.array_equal(got_rolls, want), (rank, len(got_rolls), len(want))
+    # the streaming form: rolls handed over from host memory, exchange on a side stream, result collected later
+    g = sharding.AsyncRollGather(hi - lo, n, T, dev)
+    bits_host = pipeline.pack_roll(probs, 0.5).cpu()
+    t0 = g.submit(bits_host)
+    t1 = g.submit(bits_host.numpy())
+    assert np.array_equal(g.result(t0), want) and np.array_equal(g.result(t1), want)
+    g.ROWS_PER_CHUNK = 1                                           # force the "denser than the blind download" path
+    g2 = sharding.AsyncRollGather(hi - lo, n, T, dev)
+    g2.guess = 7
+    for sl in g2.slots:
+        sl["host_notes"] = sl["host_notes"][:7]
+    assert np.array_equal(g2.result(g2.submit(bits_host)), want)
     assert len(want) > 50, len(want)
     assert np.array_equal(got, want), (rank, len(got), len(want))
     assert np.array_equal(got_np, want)

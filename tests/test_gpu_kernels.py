@@ -367,6 +367,22 @@ def test_bits_notes_equals_float_notes_incl_seams():
         assert np.array_equal(got, onotes.group_notes(roll))
 
 
+def test_async_roll_gather_single_process():
+    from music_transcription_b200 import pipeline, sharding
+    T, n = 70, 5
+    p = torch.rand(n, 88, T, device=DEV)
+    p[:, 3, :] = 0.9
+    want = pipeline.extract_notes(p, 0.5)
+    g = sharding.AsyncRollGather(n, n, T, DEV)
+    bits = pipeline.pack_roll(p, 0.5).cpu()
+    tickets = [g.submit(bits), g.submit(bits)]
+    with pytest.raises(RuntimeError):
+        g.submit(bits)                                            # both slots in flight
+    for t in tickets:
+        assert np.array_equal(g.result(t), want)
+    assert np.array_equal(g.result(g.submit(bits)), want)        # slots are reusable
+
+
 def test_threshold_notes_takes_caller_scratch_and_rejects_a_short_one():
     L = _lib.lib()
     assert L.amt_threshold_notes_scratch_ints(3, 88) == 2 * 3 * 88
