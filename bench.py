@@ -227,7 +227,8 @@ def workload_config(args, world, n_local, batches):
                 "the stitched note list of the whole recording")
     return {"workload": what, "recording_chunks": args.chunks * world if args.chunks else args.recording,
             "chunks_per_gpu": n_local, "batches_per_gpu": [b - a for a, b in batches], "samples_per_chunk": N_SAMPLES,
-            "frames": T_FRAMES, "threshold": 0.5, "precision": args.precision, "parallelism": f"chunk-sharded x{world}",
+            "frames": T_FRAMES, "threshold": 0.5, "precision": args.precision, "lanes": args.lanes,
+            "parallelism": f"chunk-sharded x{world}",
             "l2": "each batch streams ~190 MB of activations per chunk (>> 126 MB L2) and every step re-reads its 1.9 MB/chunk "
                   "inputs after them; no explicit flush"}
 
@@ -271,6 +272,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="weak scaling instead: this many chunks per GPU per step")
     ap.add_argument("--batch", type=int, default=64, help="largest batch of chunks one pass of the kernels takes")
     ap.add_argument("--precision", default="fast", choices=["fast", "precise"])
+    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2], help="batches in flight per GPU (2: recurrences of one overlap the tensor kernels of the other)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-chunks", type=int, default=4, help="chunks per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-chunks", type=int, default=8)
@@ -328,20 +330,53 @@ def main():
     counts = torch.empty(89, dtype=torch.int32, device=dev)
     scratch = torch.empty(2 * 88 * n_local, dtype=torch.int32, device=dev)
     result = {}
+    W32 = (T + 31) // 32
+    # two LANES: consecutive batches run on two streams, so the latency-bound recurrences of one batch (50-100 idle SMs)
+    # overlap the tensor kernels of the other; results are bitwise those of a single stream (tests)
+    lane_streams = [torch.cuda.Stream(dev) for _ in range(2)] if args.lanes == 2 else [None]
+    rolls2 = [torch.empty(n_local, 88, W32, dtype=torch.int32, device=dev) for _ in range(2)]
+    gather_dev = sharding.AsyncRollGather(n_local, R, T, dev)
+    counter = {"batch": 0}
 
-    def step_device():
+    def launch_step(k):
+        """All of this rank's batches of recording k -> packed rolls (sigmoid + strict float32 '>' of main.py:153-156 straight
+        into bits, 10.6 KB per chunk), then the one exchange of the path, asynchronously: all-gather the packed rolls over
+        NCCL / NVLink, ONE grouping pass over the gathered roll on the GPU (seams between chunks, batches and ranks merge in
+        the kernel), note list -> pinned host memory on every rank."""
+        out, evs = rolls2[k & 1], []
         for a, b in batches:
-            mel = fe.logmel(wav[a:b])
-            logits = model(mel)
-            # sigmoid + strict float32 '>' (main.py:153-156), straight into the bit-packed roll (10.6 KB per chunk)
+            lane = lane_streams[counter["batch"] % len(lane_streams)]
+            counter["batch"] += 1
+            cur = lane if lane is not None else torch.cuda.current_stream(dev)
+            with torch.cuda.stream(cur):
+                logits = model(fe.logmel(wav[a:b]))
+                _lib.check(L.amt_pack_roll_u32(_lib.ptr(logits), (b - a) * 88, T, 0.5, 1, _lib.ptr(out[a:b]), cur.cuda_stream))
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                evs.append(ev)
+        return gather_dev.submit(out, after=evs)
+
+    def run_device(steps):
+        """K recordings back to back; recording k+1 is launched before the note list of recording k is collected (the host
+        never idles the GPU), and every recording's list reaches the host inside the timed region."""
+        pending = None
+        for k in range(steps):
+            t = launch_step(k)
+            if pending is not None:
+                result["notes"] = gather_dev.result(pending)
+            pending = t
+        result["notes"] = gather_dev.result(pending)
+
+    def step_sequential():
+        """The same work on ONE stream with a synchronous exchange -- used for the per-stage event pass (clean kernel times)."""
+        for a, b in batches:
+            logits = model(fe.logmel(wav[a:b]))
             _lib.check(L.amt_pack_roll_u32(_lib.ptr(logits), (b - a) * 88, T, 0.5, 1, _lib.ptr(rolls[a:b]), stream))
-        # the one exchange of the path: all-gather the packed rolls over NCCL / NVLink, group the gathered roll once on
-        # the GPU (seams between chunks, batches and ranks merge in the kernel), note list -> host on every rank
-        result["notes"] = sharding.gather_rolls_notes(rolls, T, R)
+        result["notes_seq"] = sharding.gather_rolls_notes(rolls, T, R)
 
     # End to end through the public API with HOST buffers: pipeline.StreamingTranscriber copies batch i+1 in and batch i-1
     # out while batch i computes; every batch still moves its own audio in and its rolls + notes out.
-    streamer = pipeline.StreamingTranscriber(model, B0, N_SAMPLES, 0.5, input_format="pcm16", roll_format="bits")
+    streamer = pipeline.StreamingTranscriber(model, B0, N_SAMPLES, 0.5, input_format="pcm16", roll_format="bits", lanes=args.lanes)
     e2e_stats = {"d2h": 0}
 
     rec_bits = torch.zeros(n_local, 88, (T + 31) // 32, dtype=torch.int32)        # this rank's packed rolls of one recording (host)
@@ -372,12 +407,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, loop=True):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        if loop:
+            for _ in range(steps):
+                fn()
+        else:
+            fn(steps)                        # fn pipelines the steps itself and returns with every result on the host
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -385,8 +423,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 1)):
-        step_device()
+    run_device(max(args.warmup, 1))
     torch.cuda.synchronize()
 
     # ---- end to end with host buffers (the headline; measured first, right after warm-up)
@@ -414,7 +451,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = L.amt_launch_count()
-    ms = timed(step_device, args.steps)
+    ms = timed(run_device, args.steps, loop=False)
     launches = int(L.amt_launch_count() - launches0)
     clocks = sampler.stop()
     value = R * args.steps / (ms / 1e3)
@@ -422,8 +459,11 @@ def main():
     same = bool(np.array_equal(result["notes"], result["e2e_notes"]))           # the two paths saw the same samples
 
     # ---- the same K steps again with CUDA events around every kernel launch: the per-stage breakdown
+    step_sequential()
+    ms_seq = timed(step_sequential, args.steps)
+    seq_same = bool(np.array_equal(result["notes_seq"], result["notes"]))
     model.profile(True)
-    timed(step_device, args.steps)
+    timed(step_sequential, args.steps)
     stages = model.profile_read()
     model.profile(False)
 
@@ -521,7 +561,10 @@ def main():
                         "notes_equal_device_path": same},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "model_tflops_whole_step": round(total_flops * args.steps / (ms / 1e3) / 1e12, 2),
-                "stages": per_stage, "notes_per_recording": n_notes, "gathered_equals_single_rank": verified}
+                "stages": per_stage, "notes_per_recording": n_notes, "gathered_equals_single_rank": verified,
+                "single_stream": {"value": round(R * args.steps / (ms_seq / 1e3), 3), "ms_per_step": round(ms_seq / args.steps, 3),
+                                  "what": "the same steps on ONE stream with a synchronous exchange (lanes = 1, no step pipelining); the "
+                                          "per-stage times and the roofline kernel's TFLOP/s come from this form", "notes_equal": seq_same}}
         side = {}
         if sweep:
             side["configs[4]_threshold_sweep"] = sweep

@@ -294,8 +294,10 @@ def unpack_roll(bits, T: int) -> np.ndarray:
 class StreamingTranscriber:
     """Host buffers in, host piano-rolls + note lists out, batch after batch, with the copies of batch i+1
     (pinned host audio -> device) and of batch i-1 (rolls and notes -> pinned host) overlapped with the compute
-    of batch i: three CUDA streams, two buffer slots.  This is the end-to-end form of main.py:258-275 for a
-    long recording -- every batch still pays its H2D and D2H, they just no longer sit on the critical path.
+    of batch i, and -- ``lanes=2`` -- TWO batches computing at once on two streams, so that the latency-bound LSTM
+    recurrences of one (which leave 50-100 of the 148 SMs idle) run beside the tensor kernels of the other (-11 % time per
+    batch, measured; results are bitwise those of one lane).  This is the end-to-end form of main.py:258-275 for a long
+    recording -- every batch still pays its H2D and D2H, they just no longer sit on the critical path.
 
         st = StreamingTranscriber(model, chunks_per_batch=64, input_format="pcm16")
         for roll_bits, notes in st.run(pinned_batches):
@@ -307,22 +309,25 @@ class StreamingTranscriber:
     ``roll_format``: "bits" (default) -- the roll leaves the device bit-packed, int32 (c, 88, ceil(T/32)),
         10.6 KB instead of 330 KB per chunk (``unpack_roll`` restores the float array); "f32" -- the float {0,1} roll
         of main.py:153-160 itself.
-    LIFETIME: each yielded (roll, notes) pair is a VIEW into one of two reused pinned slots and is valid until the
-    next-but-one batch is launched, i.e. until the generator is advanced again -- consume or copy it inside the loop
-    body (``copy=True`` yields private copies instead, for ``list(st.run(...))``).
+    ``lanes``: batches in flight on the GPU (1 or 2).  Results come out in input order either way.
+    LIFETIME: each yielded (roll, notes) pair is a VIEW into one of ``2 * lanes`` reused pinned slots and is valid until
+    the generator is advanced again -- consume or copy it inside the loop body (``copy=True`` yields private copies
+    instead, for ``list(st.run(...))``).
     ``notes`` are grouped per batch (frame indices relative to the batch); ``sharding.stitch_notes`` merges
-    batches / ranks exactly like grouping the concatenated roll."""
+    batches / ranks exactly like grouping the concatenated roll, ``sharding.AsyncRollGather`` does it from the packed rolls."""
 
     class _Slot:
         pass
 
     def __init__(self, model, chunks_per_batch: int, n_samples: int = int(CHUNK_LENGTH * SR), threshold: float = THRESHOLD,
                  sr=SR, n_mels=N_MELS, hop_length=HOP_LENGTH, input_format: str = "f32", roll_format: str = "bits",
-                 copy: bool = False):
+                 copy: bool = False, lanes: int = 1):
         if input_format not in ("f32", "pcm16") or roll_format not in ("bits", "f32"):
             raise ValueError("StreamingTranscriber: input_format in {'f32','pcm16'}, roll_format in {'bits','f32'}")
+        if lanes not in (1, 2):
+            raise ValueError("StreamingTranscriber: lanes must be 1 or 2")
         self.model, self.C, self.thr = model, chunks_per_batch, float(threshold)
-        self.input_format, self.roll_format, self.copy = input_format, roll_format, copy
+        self.input_format, self.roll_format, self.copy, self.lanes = input_format, roll_format, copy, lanes
         dev = torch.device(model.device)
         _lib.require_cuda(torch.empty(0, device=dev), "StreamingTranscriber device")
         self.dev = dev
@@ -333,8 +338,13 @@ class StreamingTranscriber:
         W = (T + 31) // 32
         cap = 88 * ((C * T + 1) // 2)
         self.copy_in, self.copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        # the note list is fetched in a second step (its length must reach the host first); on its own stream, so that it
+        # never queues behind the roll download of a LATER batch that is still computing
+        self.copy_notes = torch.cuda.Stream(dev)
+        # lanes == 1 computes on the caller's current stream (as before); lanes == 2 on two streams of its own
+        self.lane_streams = [torch.cuda.Stream(dev) for _ in range(lanes)] if lanes > 1 else [None]
         self.slots = []
-        for _ in range(2):
+        for _ in range(2 * lanes):
             s = StreamingTranscriber._Slot()
             s.wav = torch.empty(C, n_samples, device=dev)
             s.pcm = torch.empty(C, n_samples, dtype=torch.int16, device=dev) if input_format == "pcm16" else None
@@ -357,8 +367,9 @@ class StreamingTranscriber:
         self.roll_bytes = s.host_roll.numel() * 4 + 89 * 4
 
     def _launch(self, i: int, host_wav: torch.Tensor) -> None:
-        s = self.slots[i & 1]
-        compute = torch.cuda.current_stream(self.dev)
+        s = self.slots[i % len(self.slots)]
+        lane = self.lane_streams[i % self.lanes]
+        compute = lane if lane is not None else torch.cuda.current_stream(self.dev)
         n = host_wav.shape[0]
         want = torch.int16 if self.input_format == "pcm16" else torch.float32
         if host_wav.dtype != want or host_wav.shape[1] != self.n_samples or n > self.C:
@@ -370,23 +381,21 @@ class StreamingTranscriber:
             self.copy_in.wait_event(s.compute_done)             # the compute that last read this slot's audio is done
             (s.pcm if s.pcm is not None else s.wav)[:n].copy_(host_wav, non_blocking=True)
             s.h2d_done.record(self.copy_in)
-        compute.wait_event(s.h2d_done)
-        compute.wait_event(s.d2h_done)                          # this slot's previous results have left the device
-        with torch.cuda.device(self.dev):
+        with torch.cuda.device(self.dev), torch.cuda.stream(compute):
+            compute.wait_event(s.h2d_done)
+            compute.wait_event(s.d2h_done)                      # this slot's previous results have left the device
+            sp = compute.cuda_stream
             if s.pcm is not None:
-                _lib.check(L.amt_pcm16_to_mono_f32(_lib.ptr(s.pcm), n * self.n_samples, 1, _lib.ptr(s.wav), _lib.stream_ptr(self.dev)))
+                _lib.check(L.amt_pcm16_to_mono_f32(_lib.ptr(s.pcm), n * self.n_samples, 1, _lib.ptr(s.wav), sp))
             mel = self.fe.logmel(s.wav[:n])
             logits = self.model(mel)
             if self.roll_format == "f32":
-                _lib.check(L.amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), self.thr, _lib.ptr(s.probs),
-                                                   _lib.ptr(s.roll), _lib.stream_ptr(self.dev)))
+                _lib.check(L.amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), self.thr, _lib.ptr(s.probs), _lib.ptr(s.roll), sp))
             else:
-                _lib.check(L.amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), self.thr, _lib.ptr(s.probs), 0,
-                                                   _lib.stream_ptr(self.dev)))
-                _lib.check(L.amt_pack_roll_u32(_lib.ptr(s.probs), n * 88, self.T, self.thr, 0, _lib.ptr(s.roll),
-                                               _lib.stream_ptr(self.dev)))
-        extract_notes_async(s.probs[:n], self.thr, s.notes, s.counts, s.scratch)
-        s.compute_done.record(compute)
+                _lib.check(L.amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), self.thr, _lib.ptr(s.probs), 0, sp))
+                _lib.check(L.amt_pack_roll_u32(_lib.ptr(s.probs), n * 88, self.T, self.thr, 0, _lib.ptr(s.roll), sp))
+            extract_notes_async(s.probs[:n], self.thr, s.notes, s.counts, s.scratch)
+            s.compute_done.record(compute)
         with torch.cuda.stream(self.copy_out):
             self.copy_out.wait_event(s.compute_done)
             s.host_roll[:n].copy_(s.roll[:n], non_blocking=True)
@@ -394,25 +403,27 @@ class StreamingTranscriber:
             s.counts_done.record(self.copy_out)
 
     def _finish(self, i: int):
-        s = self.slots[i & 1]
-        s.counts_done.synchronize()                             # host waits; the GPU is already on the next batch
+        s = self.slots[i % len(self.slots)]
+        s.counts_done.synchronize()                             # host waits; the GPU is already on the next batches
         total = int(s.host_counts[88])
         if total > s.notes.shape[0]:
             raise _lib.AmtError(f"StreamingTranscriber: {total} notes exceed the buffer")
-        with torch.cuda.stream(self.copy_out):
+        with torch.cuda.stream(self.copy_notes):
+            self.copy_notes.wait_event(s.counts_done)           # (implies this batch's compute)
             s.host_notes[:total].copy_(s.notes[:total], non_blocking=True)
-            s.d2h_done.record(self.copy_out)
+            s.d2h_done.record(self.copy_notes)
         s.d2h_done.synchronize()
         roll, notes = s.host_roll[:s.n], s.host_notes[:total].numpy()
         return (roll.clone(), notes.copy()) if self.copy else (roll, notes)
 
     def run(self, host_batches):
         """host_batches: iterable of pinned (c <= chunks_per_batch, n_samples) tensors, float32 or int16 per
-        ``input_format``.  Yields (roll, notes) per batch -- see the class docstring for formats and lifetime."""
+        ``input_format``.  Yields (roll, notes) per batch, in order -- see the class docstring for formats and lifetime."""
+        depth = self.lanes                                      # batches launched ahead of the one being collected
         i = -1
         for i, hb in enumerate(host_batches):
             self._launch(i, hb)
-            if i > 0:
-                yield self._finish(i - 1)
-        if i >= 0:
-            yield self._finish(i)
+            if i >= depth:
+                yield self._finish(i - depth)
+        for j in range(max(i - depth + 1, 0), i + 1):
+            yield self._finish(j)

@@ -219,30 +219,51 @@ class AsyncRollGather:
             self.slots.append(sl)
         self.n = 0
 
-    def submit(self, bits_host) -> int:
+    def submit(self, bits, after=()) -> int:
+        """``bits``: this rank's packed rolls int32 (n_local, 88, words) -- a HOST tensor / array (copied into a pinned
+        staging buffer and uploaded), or a CUDA tensor (used in place: keep it unchanged until ``result``).  ``after``:
+        CUDA events the exchange must wait for (e.g. the completion of the lanes that wrote a CUDA ``bits``); for a CUDA
+        ``bits`` the caller's current stream is always waited for."""
         from . import _lib
         ticket = self.n
         sl = self.slots[ticket & 1]
         if sl["busy"]:
             raise RuntimeError("AsyncRollGather: collect result(ticket - 2) before submitting again")
-        src = bits_host if torch.is_tensor(bits_host) else torch.from_numpy(np.ascontiguousarray(bits_host))
-        sl["host_bits"][:self.n_local].copy_(src.view(torch.int32).reshape(self.n_local, self.n_pitch, self.words))
+        on_device = torch.is_tensor(bits) and bits.is_cuda
+        if on_device:
+            local = bits.view(torch.int32).reshape(self.n_local, self.n_pitch, self.words)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(self.dev))
+            after = tuple(after) + (ready,)
+        else:
+            src = bits if torch.is_tensor(bits) else torch.from_numpy(np.ascontiguousarray(bits))
+            sl["host_bits"][:self.n_local].copy_(src.view(torch.int32).reshape(self.n_local, self.n_pitch, self.words))
         with torch.cuda.device(self.dev), torch.cuda.stream(self.side):
-            sl["bits"].copy_(sl["host_bits"], non_blocking=True)
+            for ev in after:
+                self.side.wait_event(ev)
+            if on_device:
+                cap = sl["bits"].shape[0]
+                send = local if (self.world == 1 or self.n_local == cap) else None
+                if send is None:
+                    sl["bits"][:self.n_local].copy_(local, non_blocking=True)
+                    send = sl["bits"]
+            else:
+                sl["bits"].copy_(sl["host_bits"], non_blocking=True)
+                send = sl["bits"]
             if self.world > 1:
-                dist.all_gather_into_tensor(sl["all"], sl["bits"])
+                dist.all_gather_into_tensor(sl["all"], send.contiguous())
                 cap = sl["all"].shape[1]
                 rolls = (sl["all"].view(self.world * cap, self.n_pitch, self.words) if min(self.sizes) == cap
                          else torch.cat([sl["all"][r, :self.sizes[r]] for r in range(self.world)]))
             else:
-                rolls = sl["bits"][:self.n_local]
+                rolls = send[:self.n_local]
             _lib.check(_lib.lib().amt_bits_notes(_lib.ptr(rolls), self.n_total, self.n_pitch, self.T, _lib.ptr(sl["notes"]), self.cap,
                                                  _lib.ptr(sl["counts"]), _lib.ptr(sl["scratch"]), sl["scratch"].numel(),
                                                  self.side.cuda_stream))
             sl["host_counts"].copy_(sl["counts"], non_blocking=True)
             sl["host_notes"].copy_(sl["notes"][:self.guess], non_blocking=True)
             sl["done"].record(self.side)
-            sl["rolls_keepalive"] = rolls
+            sl["keepalive"] = (rolls, send)
         sl["busy"] = True
         self.n += 1
         return ticket

@@ -129,6 +129,7 @@ class TranscriptionModel(nn.Module):
         self._handle = None          # amt_model*
         self._packed_key = None
         self._workspace = None
+        self._workspaces = {}        # (device, stream) -> uint8 tensor
         self.to(device)
 
     # ------------------------------------------------------------------ plumbing
@@ -196,9 +197,14 @@ class TranscriptionModel(nn.Module):
             pass
 
     def _workspace_for(self, nbytes, dev):
-        ws = self._workspace
-        if ws is None or ws.numel() < nbytes + 1024 or ws.device != dev:
-            self._workspace = ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        """One workspace PER CUDA STREAM: forwards issued on different streams may run concurrently (pipeline.
+        StreamingTranscriber keeps two in flight so that one's latency-bound recurrences overlap the other's tensor
+        kernels), and each needs its own intermediates.  The packed weights (the handle) are shared."""
+        key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._workspaces.get(key)
+        if ws is None or ws.numel() < nbytes + 1024:
+            self._workspaces[key] = ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        self._workspace = ws                     # the most recently used one (workspace_tensor reads intermediates from it)
         off = (-ws.data_ptr()) % 1024
         return ws.data_ptr() + off, ws.numel() - off
 

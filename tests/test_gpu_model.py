@@ -444,8 +444,31 @@ def test_two_hour_recording_240_chunks_batch_invariance_and_notes():
     assert torch.equal(solo[0], batch[4])
 
 
-@pytest.mark.parametrize("input_format,roll_format", [("f32", "f32"), ("pcm16", "bits"), ("f32", "bits")])
-def test_streaming_transcriber_equals_batch_by_batch_path(input_format, roll_format):
+def test_two_forwards_in_flight_on_two_streams_are_bitwise_one_stream():
+    """One model object used from two CUDA streams at once (what StreamingTranscriber(lanes=2) does): every stream gets its
+    own workspace, the packed weights are shared, and the results are bitwise those of a single stream -- on the
+    north-star model, whose recurrences then overlap the other stream's tensor kernels."""
+    sd = synth.synth_state_dict("cnn_rnn_large", 320, 512, 3, seed=1, gain=3 ** -0.5)
+    m = TranscriptionModel("cnn_rnn_large", n_mels=320, hidden_size=512, num_layers=3, dropout=0.2, device=DEV).eval()
+    m.load_state_dict(sd)
+    fe = pipeline.Frontend.get(device=DEV)
+    wavs = [torch.from_numpy(synth.piano_chord_batch(range(4 * k, 4 * k + 4))).to(DEV) for k in range(2)]
+    ref = [m(fe.logmel(w)).clone() for w in wavs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(DEV), torch.cuda.Stream(DEV)]
+    outs = []
+    for rep in range(6):
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                outs.append((k, m(fe.logmel(wavs[k]))))
+    torch.cuda.synchronize()
+    assert len(m._workspaces) >= 3                              # the default stream's and one per lane
+    for k, o in outs:
+        assert torch.equal(o, ref[k])
+
+
+@pytest.mark.parametrize("input_format,roll_format,lanes", [("f32", "f32", 1), ("pcm16", "bits", 1), ("f32", "bits", 2), ("pcm16", "bits", 2)])
+def test_streaming_transcriber_equals_batch_by_batch_path(input_format, roll_format, lanes):
     """Overlapped H2D / compute / D2H (3 streams, 2 slots) must return exactly what the plain per-batch path does,
     including a short last batch and slot reuse (5 batches over 2 slots) -- for float32 and 16-bit PCM input (the
     on-device conversion is bit-identical to sample / 32768 on the host) and for the float and the bit-packed roll."""
@@ -460,7 +483,7 @@ def test_streaming_transcriber_equals_batch_by_batch_path(input_format, roll_for
         feed = pcm
     else:
         feed = [b.pin_memory() for b in batches]
-    st = pipeline.StreamingTranscriber(m, 4, 480000, 0.5, input_format=input_format, roll_format=roll_format)
+    st = pipeline.StreamingTranscriber(m, 4, 480000, 0.5, input_format=input_format, roll_format=roll_format, lanes=lanes)
     got = [(r.clone(), n.copy()) for r, n in st.run(feed)]
     assert len(got) == 5
     for hb, (roll, notes) in zip(batches, got):
@@ -473,7 +496,7 @@ def test_streaming_transcriber_equals_batch_by_batch_path(input_format, roll_for
         else:
             assert torch.equal(roll, want_roll)
     # copy=True hands out private copies: collecting the generator must not alias the two pinned slots
-    st2 = pipeline.StreamingTranscriber(m, 4, 480000, 0.5, input_format=input_format, roll_format=roll_format, copy=True)
+    st2 = pipeline.StreamingTranscriber(m, 4, 480000, 0.5, input_format=input_format, roll_format=roll_format, copy=True, lanes=lanes)
     kept = list(st2.run(feed))
     for (r0, n0), (r1, n1) in zip(got, kept):
         assert torch.equal(r0, r1) and np.array_equal(n0, n1)
