@@ -216,6 +216,38 @@ def gpu_eager_chunks_per_sec(mel: torch.Tensor, sd_cpu, reps: int = 3):
     return mel.shape[0] / (best / 1e3), best
 
 
+class HangGuard(threading.Thread):
+    """Safety net for the two-lane mode.  Two forwards in flight is stable (soak: 8500 batches, profiles/r2_two_lanes.md), but
+    THREE lanes, or two lanes with capped tensor grids, stop making progress on this hardware -- an unexplained
+    scheduling cliff one step away.  While armed, the guard watches a progress stamp; if the GPU phases make no progress for
+    `limit` seconds it re-executes this benchmark with --lanes 1 (exec tears the CUDA context down) instead of hanging."""
+
+    def __init__(self, limit=60.0):
+        super().__init__(daemon=True)
+        self.limit, self.armed, self.stamp = limit, False, time.time()
+
+    def tick(self):
+        self.stamp = time.time()
+
+    def arm(self, on=True):
+        self.stamp, self.armed = time.time(), on
+
+    def run(self):
+        while True:
+            time.sleep(2.0)
+            if self.armed and time.time() - self.stamp > self.limit:
+                sys.stderr.write(f"[bench] no GPU progress for {self.limit:.0f} s with --lanes 2: re-executing with --lanes 1\n")
+                sys.stderr.flush()
+                argv, skip = [], False
+                for a in sys.argv:
+                    if skip or a == "--lanes":
+                        skip = a == "--lanes"             # drop the flag and its value
+                        continue
+                    if not a.startswith("--lanes="):
+                        argv.append(a)
+                os.execv(sys.executable, [sys.executable] + argv + ["--lanes", "1", "--fell-back"])
+
+
 def workload_config(args, world, n_local, batches):
     if args.chunks:
         what = (f"weak scaling: {args.chunks} synthetic 30-s chunks per GPU per step (BASELINE configs[3]'s model and path, "
@@ -273,6 +305,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="largest batch of chunks one pass of the kernels takes")
     ap.add_argument("--precision", default="fast", choices=["fast", "precise"])
     ap.add_argument("--lanes", type=int, default=2, choices=[1, 2], help="batches in flight per GPU (2: recurrences of one overlap the tensor kernels of the other)")
+    ap.add_argument("--fell-back", action="store_true", help=argparse.SUPPRESS)      # set by HangGuard's re-exec
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-chunks", type=int, default=4, help="chunks per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-chunks", type=int, default=8)
@@ -364,8 +397,10 @@ def main():
             t = launch_step(k)
             if pending is not None:
                 result["notes"] = gather_dev.result(pending)
+                guard.tick()
             pending = t
         result["notes"] = gather_dev.result(pending)
+        guard.tick()
 
     def step_sequential():
         """The same work on ONE stream with a synchronous exchange -- used for the per-stage event pass (clean kernel times)."""
@@ -391,6 +426,7 @@ def main():
         for i, (roll, nts) in enumerate(streamer.run(feed)):
             a, b = batches[i % len(batches)]
             rec_bits[a:b].copy_(roll)
+            guard.tick()
             d2h += roll.numel() * 4 + 89 * 4 + nts.size * 4                      # what the streamer downloaded for this batch
             if i % len(batches) == len(batches) - 1:                              # the recording's last batch on this rank
                 ticket = gatherer.submit(rec_bits)
@@ -423,8 +459,13 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    guard = HangGuard()
+    if args.lanes == 2:
+        guard.start()
+        guard.arm()
     run_device(max(args.warmup, 1))
     torch.cuda.synchronize()
+    guard.tick()
 
     # ---- end to end with host buffers (the headline; measured first, right after warm-up)
     run_e2e(1)
@@ -459,6 +500,7 @@ def main():
     same = bool(np.array_equal(result["notes"], result["e2e_notes"]))           # the two paths saw the same samples
 
     # ---- the same K steps again with CUDA events around every kernel launch: the per-stage breakdown
+    guard.arm(False)                                   # everything below runs on one stream
     step_sequential()
     ms_seq = timed(step_sequential, args.steps)
     seq_same = bool(np.array_equal(result["notes_seq"], result["notes"]))
@@ -562,6 +604,7 @@ def main():
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "model_tflops_whole_step": round(total_flops * args.steps / (ms / 1e3) / 1e12, 2),
                 "stages": per_stage, "notes_per_recording": n_notes, "gathered_equals_single_rank": verified,
+                "fell_back_to_one_lane": bool(args.fell_back),
                 "single_stream": {"value": round(R * args.steps / (ms_seq / 1e3), 3), "ms_per_step": round(ms_seq / args.steps, 3),
                                   "what": "the same steps on ONE stream with a synchronous exchange (lanes = 1, no step pipelining); the "
                                           "per-stage times and the roofline kernel's TFLOP/s come from this form", "notes_equal": seq_same}}

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 ncu evidence (1 GPU).  Outputs -> gpurun_out/ ; summarised by tools/summarize_ncu.py into profiles/.
 mkdir -p gpurun_out
-SMALL="python bench.py --steps 2 --warmup 1 --no-configs --no-cpu-baseline"
+SMALL="python bench.py --steps 2 --warmup 1 --no-configs --no-cpu-baseline --lanes 1"
 $SMALL > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_launches.csv $SMALL > gpurun_out/ncu_launches.log 2>&1
 tail -2 gpurun_out/ncu_launches.log
