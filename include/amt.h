@@ -123,6 +123,13 @@ int amt_model_workspace_layout(const amt_model* m, int B, int T, const char* nam
  * amt_model_workspace_bytes(m,B,T) bytes, 1024-byte aligned. */
 int amt_model_forward(amt_model* m, const float* logmel, int B, int T, float* frame, float* onset,
                       float* offset, void* workspace, size_t workspace_bytes, amt_stream_t stream);
+/* The same forward fed by amt_logmel_f32(..., top_db < 0, chunk_max): `logmel` is the UNFLOORED dB spectrogram and the
+ * per-chunk floor max(x, chunk_max[b] - top_db) of librosa.power_to_db (reference main.py:125) is applied by the stem
+ * convolution as it loads its input -- bitwise the result of flooring first, without the extra read + write of the
+ * spectrogram.  chunk_max: [B] f32 device (as written by amt_logmel_f32); NULL = `logmel` is already floored. */
+int amt_model_forward_db(amt_model* m, const float* logmel, const float* chunk_max, float top_db, int B, int T,
+                         float* frame, float* onset, float* offset, void* workspace, size_t workspace_bytes,
+                         amt_stream_t stream);
 
 /* Per-stage device timing of amt_model_forward (CUDA events on the caller's stream around every
  * kernel launch).  enable != 0 starts/resets accumulation; read synchronises the pending events

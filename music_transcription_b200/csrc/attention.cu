@@ -186,7 +186,9 @@ int run_attention(const void* qkv, void* out, int B, int T, int heads, int head_
   AMT_TRY(ensure_device());
   AMT_REQUIRE(B > 0 && T > 0 && heads > 0, "attention: empty problem");
   static const bool force_sync = getenv("AMT_ATT_MMA_SYNC") != nullptr;    // bring-up switch
-  if (!force_sync && (head_dim == 64 || head_dim == 128 || head_dim == 192))
+  // every head dim of the path (48 / 96 / 144 / 192 = hidden 128 .. 512) runs the tcgen05 kernel, padded to the
+  // next multiple of 64 by the tensor maps' zero fill; the mma.sync kernel below stays as a bring-up cross-check
+  if (!force_sync && head_dim % 8 == 0 && head_dim <= 192)
     return run_attention_tc(qkv, out, B, T, heads, head_dim, clip, stream);
   switch (head_dim) {
     case 48: return launch_attention<48>(qkv, out, B, T, heads, clip, stream);

@@ -162,7 +162,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       ptx::mbar_wait(q_empty, (tl & 1) ^ 1);
       if (leader) {
         ptx::mbar_expect_tx(q_full, Cfg::kQBytes);
-        for (int i = 0; i < NB; ++i) ptx::tma_load_3d(q_smem + i * (kAttQ * 128), &tmQ, q_full, head * HD + i * 64, t0, b);
+        for (int i = 0; i < NB; ++i) ptx::tma_load_4d(q_smem + i * (kAttQ * 128), &tmQ, q_full, i * 64, head, t0, b);
       }
       __syncwarp();
       for (int j = 0; j < p.nb; ++j) {
@@ -170,7 +170,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (leader) {
           ptx::mbar_expect_tx(&k_full[s], Cfg::kKVBytes);
           for (int i = 0; i < NB; ++i)
-            ptx::tma_load_3d(k_smem + s * Cfg::kKVBytes + i * (kAttK * 128), &tmKV, &k_full[s], p.D + head * HD + i * 64,
+            ptx::tma_load_4d(k_smem + s * Cfg::kKVBytes + i * (kAttK * 128), &tmKV, &k_full[s], i * 64, p.heads + head,
                              j * kAttK, b);
         }
         __syncwarp();
@@ -178,8 +178,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (leader) {
           ptx::mbar_expect_tx(&v_full[s], Cfg::kKVBytes);
           for (int i = 0; i < NB; ++i)
-            ptx::tma_load_3d(v_smem + s * Cfg::kKVBytes + i * (kAttK * 128), &tmKV, &v_full[s],
-                             2 * p.D + head * HD + i * 64, j * kAttK, b);
+            ptx::tma_load_4d(v_smem + s * Cfg::kKVBytes + i * (kAttK * 128), &tmKV, &v_full[s], i * 64, 2 * p.heads + head,
+                             j * kAttK, b);
         }
         __syncwarp();
         if (++s == kAttStages) { s = 0; ph ^= 1; }
@@ -401,7 +401,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (issuer) ptx::bulk_wait_group_read0();  // (the buffer written next was read by the store one chunk ago)
         ptx::named_bar_sync(1, kAttSoftThreads);
         if (issuer) {
-          ptx::tma_store_3d(&tmO, obuf, head * HD + cc * 64, t0, b);
+          ptx::tma_store_4d(&tmO, obuf, cc * 64, head, t0, b);
           ptx::bulk_commit_group();
         }
       }
@@ -422,24 +422,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+// HD = head dim padded to a multiple of 64 (the kernel's tile width), hd = the real one (48 / 96 / 144 / 192 for
+// hidden 128 .. 512).  The tensor maps describe qkv as [B][T][3 * heads][hd] and the output as [B][T][heads][hd] with
+// the REAL hd as the innermost extent: a 64-wide box that reaches past hd is zero-filled on load (the padded q / k
+// columns add 0 to every score, the padded v columns produce zeros) and clipped on store.
 template <int HD>
-static int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, float clip, cudaStream_t stream) {
+static int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, int hd, float clip, cudaStream_t stream) {
   using Cfg = AttCfg<HD>;
+  AMT_REQUIRE(hd <= HD && hd > HD - 64 && hd % 8 == 0, "attention (tcgen05): head_dim %d does not pad to %d", hd, HD);
   AMT_FUNC_ATTR(attention_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-  const int D = heads * HD;
+  const int D = heads * hd;
   CUtensorMap tq, tkv, to;
   {
-    uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)T, (uint64_t)B};
-    uint64_t str[2] = {(uint64_t)3 * D * 2, (uint64_t)T * 3 * D * 2};
-    uint32_t boxq[3] = {64, kAttQ, 1}, boxk[3] = {64, kAttK, 1};
-    AMT_TRY(encode_tmap_bf16(&tq, qkv, 3, dims, str, boxq, CU_TENSOR_MAP_SWIZZLE_128B));
-    AMT_TRY(encode_tmap_bf16(&tkv, qkv, 3, dims, str, boxk, CU_TENSOR_MAP_SWIZZLE_128B));
+    uint64_t dims[4] = {(uint64_t)hd, (uint64_t)3 * heads, (uint64_t)T, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)hd * 2, (uint64_t)3 * D * 2, (uint64_t)T * 3 * D * 2};
+    uint32_t boxq[4] = {64, 1, kAttQ, 1}, boxk[4] = {64, 1, kAttK, 1};
+    AMT_TRY(encode_tmap_bf16(&tq, qkv, 4, dims, str, boxq, CU_TENSOR_MAP_SWIZZLE_128B));
+    AMT_TRY(encode_tmap_bf16(&tkv, qkv, 4, dims, str, boxk, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   {
-    uint64_t dims[3] = {(uint64_t)D, (uint64_t)T, (uint64_t)B};
-    uint64_t str[2] = {(uint64_t)D * 2, (uint64_t)T * D * 2};
-    uint32_t box[3] = {64, kAttQ, 1};
-    AMT_TRY(encode_tmap_bf16(&to, out, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    uint64_t dims[4] = {(uint64_t)hd, (uint64_t)heads, (uint64_t)T, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)hd * 2, (uint64_t)D * 2, (uint64_t)T * D * 2};
+    uint32_t box[4] = {64, 1, kAttQ, 1};
+    AMT_TRY(encode_tmap_bf16(&to, out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   AttParams p;
   p.T = T;
@@ -451,7 +456,7 @@ static int launch_attention_tc(const void* qkv, void* out, int B, int T, int hea
   p.num_tiles = static_cast<int>(nt);
   p.nb = ceil_div(T, kAttK);
   p.D = D;
-  p.scale = 1.0f / sqrtf(static_cast<float>(HD));
+  p.scale = 1.0f / sqrtf(static_cast<float>(hd));
   p.clip = clip;
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   p.trace = nullptr;
@@ -469,7 +474,7 @@ static int launch_attention_tc(const void* qkv, void* out, int B, int T, int hea
     AMT_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
     const int tiles0 = (p.num_tiles + grid - 1) / grid;
     fprintf(stderr, "[att trace] B=%d T=%d hd=%d tiles/CTA=%d blocks/tile=%d\n  mma : qt_full %lld k_full %lld s_empty %lld S-issue %lld p_full %lld v_full %lld o_empty %lld PV-issue %lld total %lld\n",
-            B, T, HD, tiles0, p.nb, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[9]);
+            B, T, hd, tiles0, p.nb, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[9]);
     for (int w = 0; w < kAttParts; ++w) {
       const long long* t = h + 10 + 10 * w;
       fprintf(stderr, "  soft%d: q_full %lld q-copy %lld s_full %lld ld+exp %lld p_empty %lld st+arrive %lld o_full %lld epilogue %lld misc %lld total %lld\n",
@@ -481,12 +486,11 @@ static int launch_attention_tc(const void* qkv, void* out, int B, int T, int hea
 }
 
 int run_attention_tc(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip, cudaStream_t stream) {
-  switch (head_dim) {
-    case 64: return launch_attention_tc<64>(qkv, out, B, T, heads, clip, stream);
-    case 128: return launch_attention_tc<128>(qkv, out, B, T, heads, clip, stream);
-    case 192: return launch_attention_tc<192>(qkv, out, B, T, heads, clip, stream);
-    default: return set_error(AMT_ERR_ARG, "attention (tcgen05): head_dim %d unsupported", head_dim);
-  }
+  AMT_REQUIRE(head_dim >= 8 && head_dim <= 192 && head_dim % 8 == 0,
+              "attention (tcgen05): head_dim %d unsupported (a multiple of 8 up to 192)", head_dim);
+  if (head_dim <= 64) return launch_attention_tc<64>(qkv, out, B, T, heads, head_dim, clip, stream);
+  if (head_dim <= 128) return launch_attention_tc<128>(qkv, out, B, T, heads, head_dim, clip, stream);
+  return launch_attention_tc<192>(qkv, out, B, T, heads, head_dim, clip, stream);
 }
 
 }  // namespace amt

@@ -23,15 +23,19 @@ constexpr int kHalf = 1024;
 constexpr int kFramesPerCta = 8;
 constexpr int kWarpsPerCta = 8;
 
+constexpr int kMaxRounds = 32;   // n_mels <= 1024: rounds of 32 filters (one per lane)
 struct FrontendDev {
-  const float* window;     // [2048] periodic Hann (fp64 -> fp32)
   const float2* tw1024;    // [1024] exp(-2*pi*i*k/1024)
   const float2* tw2048;    // [1025] exp(-2*pi*i*k/2048)
-  const int* fb_start;     // [n_mels] first FFT bin of each filter
-  const int* fb_off;       // [n_mels+1] CSR offsets into fb_w
-  const float* fb_w;       // non-zero weights
-  int n_mels, hop, fb_nnz;
+  const int* fb_start;     // [rounds * 32] first FFT bin of each filter (0 for the padding filters of the last round)
+  // banded filterbank in ELL form: round r = filters 32r .. 32r+31, taps[r] = its widest band; the weight of tap i
+  // of filter 32r + l sits at fb_w[(off[r] + i) * 32 + l] (zero past the filter's own band), so a warp reads one
+  // contiguous 128-byte row per tap
+  const float* fb_w;
+  int n_mels, hop, rounds, fb_rows;          // fb_rows = sum of taps[]
+  unsigned short taps[kMaxRounds], off[kMaxRounds];
 };
+constexpr int kPowFloats = 1025 + 1025 / 32 + 32;   // padded power spectrum: bin b at b + b/32, + 31 bins a zero-weight tap may touch
 
 // ---- 32-point in-register FFT (radix-2 DIF, output in bit-reversed order) ----
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -73,18 +77,16 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
-logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples, int T, FrontendDev fe,
+logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples, int T, const __grid_constant__ FrontendDev fe,
               float* __restrict__ out, float* __restrict__ chunk_max, int vec_ok) {
   extern __shared__ __align__(16) uint8_t smem_fe[];
+  constexpr int kOutPitch = kFramesPerCta + 1;                      // odd pitch: lanes (= filters) hit different banks
   const int span = (kFramesPerCta - 1) * fe.hop + kNfft;            // samples shared by the CTA's frames
   float* s_x = reinterpret_cast<float*>(smem_fe);                   // [span]
   float2* s_z = reinterpret_cast<float2*>(s_x + ((span + 3) & ~3));  // [warps][32*33] transpose / spectrum / power
-  float* s_out = reinterpret_cast<float*>(s_z + kWarpsPerCta * 32 * 33);   // [n_mels][8]
-  // the banded filterbank (CSR: start bin, offsets, weights) staged in smem: lanes walk different filters, so
-  // reading it from global is a 32-address gather per tap; from shared memory it is a 2-4-way bank conflict
-  int* s_fb_start = reinterpret_cast<int*>(s_out + fe.n_mels * kFramesPerCta);   // [n_mels]
-  int* s_fb_off = s_fb_start + fe.n_mels;                                        // [n_mels + 1]
-  float* s_fb_w = reinterpret_cast<float*>(s_fb_off + fe.n_mels + 1);            // [fb_nnz]
+  float* s_out = reinterpret_cast<float*>(s_z + kWarpsPerCta * 32 * 33);   // [rounds * 32][9]
+  int* s_fb_start = reinterpret_cast<int*>(s_out + fe.rounds * 32 * kOutPitch);   // [rounds * 32]
+  float* s_fb_w = reinterpret_cast<float*>(s_fb_start + fe.rounds * 32);          // [fb_rows][32]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
@@ -105,13 +107,14 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  // (filterbank tables: L2-resident, loaded while the samples are in flight)
-  auto cp4 = [](void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ptx::smem_u32(dst)), "l"(src) : "memory");
-  };
-  for (int i = tid; i < fe.n_mels; i += blockDim.x) cp4(s_fb_start + i, fe.fb_start + i);
-  for (int i = tid; i <= fe.n_mels; i += blockDim.x) cp4(s_fb_off + i, fe.fb_off + i);
-  for (int i = tid; i < fe.fb_nnz; i += blockDim.x) cp4(s_fb_w + i, fe.fb_w + i);
+  // (filterbank tables: L2-resident, 16-byte copies issued while the samples are in flight)
+  {
+    const int n16 = (fe.rounds * 32 + fe.fb_rows * 32) >> 2;   // s_fb_start and s_fb_w are contiguous in both places
+    const float4* src = reinterpret_cast<const float4*>(fe.fb_start);
+    for (int i = tid; i < n16; i += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(reinterpret_cast<float4*>(s_fb_start) + i)), "l"(src + i)
+                   : "memory");
+  }
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (!vec_ok) {
@@ -130,7 +133,15 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
   __syncthreads();
 
   float2* zw = s_z + warp * 32 * 33;
+  float* pw = reinterpret_cast<float*>(zw);          // the same words, later: the padded power spectrum
   float wmax = -INFINITY;
+  // Periodic Hann window without a table: sample n = 64 n1 + 2 lane + j has
+  //   w = 0.5 - 0.5 cos(2 pi n1 / 32 + beta_j),  beta_j = 2 pi (2 lane + j) / 2048
+  //     = 0.5 - cos(a) * (0.5 cos beta_j) + sin(a) * (0.5 sin beta_j)
+  // cos(a), sin(a) are the radix-32 twiddles (constant bank, n1 is a compile-time index); the two beta terms are four
+  // registers per lane for the whole kernel.  Two FMAs per sample instead of 32 eight-byte table gathers per frame.
+  const float2 tb0 = __ldg(fe.tw2048 + 2 * lane), tb1 = __ldg(fe.tw2048 + 2 * lane + 1);   // (cos beta, -sin beta)
+  const float hc0 = 0.5f * tb0.x, hs0 = -0.5f * tb0.y, hc1 = 0.5f * tb1.x, hs1 = -0.5f * tb1.y;
 
   for (int fi = warp; fi < kFramesPerCta; fi += kWarpsPerCta) {
     const int t = t0 + fi;
@@ -142,8 +153,12 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
       for (int n1 = 0; n1 < 32; ++n1) {
         const int n = 64 * n1 + 2 * lane;
         const float2 xs = *reinterpret_cast<const float2*>(fx + n);
-        const float2 w = __ldg(reinterpret_cast<const float2*>(fe.window + n));
-        v[n1] = make_float2(xs.x * w.x, xs.y * w.y);
+        // (cos a, sin a) for a = 2 pi n1 / 32: c_tw32[k] = (cos, -sin)(2 pi k / 32), and a + pi flips both signs
+        const float ca = n1 < 16 ? c_tw32[n1 & 15].x : -c_tw32[n1 & 15].x;
+        const float sa = n1 < 16 ? -c_tw32[n1 & 15].y : c_tw32[n1 & 15].y;
+        const float w0 = fmaf(-ca, hc0, fmaf(sa, hs0, 0.5f));
+        const float w1 = fmaf(-ca, hc1, fmaf(sa, hs1, 0.5f));
+        v[n1] = make_float2(xs.x * w0, xs.y * w1);
       }
       fft32(v);                                           // over n1 -> k1 (bit-reversed slots)
       // twiddle W_1024^(n2*k1), then transpose through smem: zw[k1][n2]
@@ -167,34 +182,55 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
 #pragma unroll
       for (int sidx = 0; sidx < 32; ++sidx) zw[bitrev5(sidx) * 32 + lane] = v[sidx];   // natural order, k = k1 + 32*k2
       __syncwarp();
-      // real-FFT recovery in place.  With a = Z[k], c = Z[1024-k] (Z[1024] == Z[0]):
+      // real-FFT recovery.  With a = Z[k], c = Z[1024-k] (Z[1024] == Z[0]):
       //   E = (a + conj c)/2,  O = (a - conj c)/(2i),  X[k] = E + W_2048^k O,  X[1024-k] = conj(E - W_2048^k O)
-      // so one pass over k = 0..512 yields both |X[k]|^2 and |X[1024-k]|^2; the pair is written back as
-      // float2 into slot k -- which only this lane reads (slot 1024-k, k <= 512, belongs to no other k).
-      for (int k = lane; k <= kHalf / 2; k += 32) {
-        const float2 a = zw[k];
-        const float2 c = zw[(kHalf - k) & 1023];
-        const float2 e = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
-        const float2 o = make_float2(0.5f * (a.y + c.y), -0.5f * (a.x - c.x));   // (a - conj(c)) / (2i)
-        const float2 w = __ldg(fe.tw2048 + k);
-        const float2 wo = make_float2(o.x * w.x - o.y * w.y, o.x * w.y + o.y * w.x);
-        const float px = e.x + wo.x, py = e.y + wo.y, qx = e.x - wo.x, qy = e.y - wo.y;
-        zw[k] = make_float2(px * px + py * py, qx * qx + qy * qy);     // (|X[k]|^2, |X[1024-k]|^2)
+      // so one pass over k = 0..512 yields both |X[k]|^2 and |X[1024-k]|^2.  The 17 pairs of a lane stay in the
+      // registers the FFT no longer needs until every lane has read its Z values; then the power spectrum
+      // overwrites Z as a plain float array, bin b at word b + b/32 (the padding makes the filterbank's strided
+      // gathers below conflict-free for every filter spacing).
+      float pk[17], qk[17];
+#pragma unroll
+      for (int i = 0; i < 17; ++i) {
+        const int k = 32 * i + lane;
+        if (k <= kHalf / 2) {
+          const float2 a = zw[k];
+          const float2 c = zw[(kHalf - k) & 1023];
+          const float2 e = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
+          const float2 o = make_float2(0.5f * (a.y + c.y), -0.5f * (a.x - c.x));   // (a - conj(c)) / (2i)
+          const float2 w = __ldg(fe.tw2048 + k);
+          const float2 wo = make_float2(o.x * w.x - o.y * w.y, o.x * w.y + o.y * w.x);
+          const float px = e.x + wo.x, py = e.y + wo.y, qx = e.x - wo.x, qy = e.y - wo.y;
+          pk[i] = px * px + py * py;                       // |X[k]|^2
+          qk[i] = qx * qx + qy * qy;                       // |X[1024-k]|^2
+        }
       }
       __syncwarp();
-      // banded mel projection + dB.  power(j) = j <= 512 ? zw[j].x : zw[1024-j].y
-      const float* pf = reinterpret_cast<const float*>(zw);
-      for (int m = lane; m < fe.n_mels; m += 32) {
-        const int o0 = s_fb_off[m], o1 = s_fb_off[m + 1];
-        float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 17; ++i) {
+        const int k = 32 * i + lane;
+        if (k <= kHalf / 2) {
+          const int k2 = kHalf - k;
+          pw[k + (k >> 5)] = pk[i];
+          pw[k2 + (k2 >> 5)] = qk[i];                      // (k = 512 writes the same value twice)
+        }
+      }
+      pw[1025 + 1025 / 32 + lane] = 0.0f;                  // words a zero-weight tap past bin 1024 may read: no NaN * 0
+      __syncwarp();
+      // banded mel projection + dB: lane l of round r owns filter 32r + l
+      const float* wrow = s_fb_w + lane;
+      for (int r = 0; r < fe.rounds; ++r) {
+        const int m = 32 * r + lane;
         const int st = s_fb_start[m];
-        for (int j = o0; j < o1; ++j) {                    // power(bin) = bin <= 512 ? zw[bin].x : zw[1024-bin].y
-          const int bin = st + j - o0;
-          acc = fmaf(s_fb_w[j], pf[bin <= kHalf / 2 ? 2 * bin : 2 * (kHalf - bin) + 1], acc);
+        const float* wr = wrow + fe.off[r] * 32;
+        const int nt = fe.taps[r];
+        float acc = 0.0f;
+        for (int i = 0; i < nt; ++i) {
+          const int bin = st + i;
+          acc = fmaf(wr[i * 32], pw[bin + (bin >> 5)], acc);
         }
         const float db = 10.0f * log10f(fmaxf(acc, 1e-10f));
-        s_out[m * kFramesPerCta + fi] = db;
-        wmax = fmaxf(wmax, db);
+        s_out[m * kOutPitch + fi] = db;
+        if (m < fe.n_mels) wmax = fmaxf(wmax, db);
       }
       __syncwarp();
     }
@@ -203,7 +239,7 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
   // coalesced-ish store of the [n_mels][8] tile
   for (int e = tid; e < fe.n_mels * kFramesPerCta; e += blockDim.x) {
     const int m = e / kFramesPerCta, fi = e - m * kFramesPerCta;
-    if (t0 + fi < T) out[(static_cast<long long>(b) * fe.n_mels + m) * T + t0 + fi] = s_out[e];
+    if (t0 + fi < T) out[(static_cast<long long>(b) * fe.n_mels + m) * T + t0 + fi] = s_out[m * kOutPitch + fi];
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
@@ -281,8 +317,10 @@ int amt_frontend_create(int sr, int n_fft, int hop, int n_mels, double fmin, dou
     const double step = (m1 - m0) / (n_mels + 1);
     mel_f[i] = mel_to_hz(i == n_mels + 1 ? m1 : m0 + step * i);
   }
-  std::vector<int> start(n_mels), off(n_mels + 1, 0);
-  std::vector<float> w;
+  // banded filters -> ELL rounds of 32 filters (see FrontendDev)
+  const int rounds = (n_mels + 31) / 32;
+  AMT_REQUIRE(rounds <= kMaxRounds, "frontend: n_mels %d exceeds %d", n_mels, 32 * kMaxRounds);
+  std::vector<int> start(rounds * 32, 0), count(rounds * 32, 0);
   int max_band = 0;
   for (int i = 0; i < n_mels; ++i) {
     const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
@@ -297,17 +335,35 @@ int amt_frontend_create(int sr, int n_fft, int hop, int n_mels, double fmin, dou
       if (vf > 0.0f) { if (first < 0) first = k; last = k; }
     }
     start[i] = first < 0 ? 0 : first;
-    const int cnt = first < 0 ? 0 : last - first + 1;
-    for (int k = 0; k < cnt; ++k) w.push_back(fe->fb_dense[static_cast<size_t>(i) * bins + first + k]);
-    off[i + 1] = off[i] + cnt;
-    max_band = std::max(max_band, cnt);
+    count[i] = first < 0 ? 0 : last - first + 1;
+    max_band = std::max(max_band, count[i]);
   }
+  int fb_rows = 0;
+  for (int r = 0; r < rounds; ++r) {
+    int taps = 0;
+    for (int l = 0; l < 32; ++l) taps = std::max(taps, count[32 * r + l]);
+    fe->dev.taps[r] = static_cast<unsigned short>(taps);
+    fe->dev.off[r] = static_cast<unsigned short>(fb_rows);
+    fb_rows += taps;
+    // a zero-weight tap past a filter's own band still reads the power spectrum: it must stay inside the padded array
+    for (int l = 0; l < 32; ++l)
+      if (start[32 * r + l] + taps > bins + 31) {
+        delete fe;
+        return set_error(AMT_ERR_ARG, "frontend: filter %d (round width %d) reaches past the spectrum", 32 * r + l, taps);
+      }
+  }
+  if (fb_rows > 65535) { delete fe; return set_error(AMT_ERR_ARG, "frontend: filterbank too wide"); }
+  std::vector<float> w(static_cast<size_t>(fb_rows) * 32, 0.0f);
+  for (int r = 0; r < rounds; ++r)
+    for (int l = 0; l < 32; ++l) {
+      const int m = 32 * r + l;
+      for (int k = 0; k < count[m]; ++k)
+        w[(static_cast<size_t>(fe->dev.off[r]) + k) * 32 + l] = fe->fb_dense[static_cast<size_t>(m) * bins + start[m] + k];
+    }
   fe->max_band = max_band;
   // tables
-  std::vector<float> window(kNfft);
   std::vector<float2> tw1024(1024), tw2048(1025);
   const double PI = 3.14159265358979323846;
-  for (int n = 0; n < kNfft; ++n) window[n] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * PI * n / kNfft));
   for (int k = 0; k < 1024; ++k) tw1024[k] = make_float2((float)std::cos(2.0 * PI * k / 1024.0), (float)-std::sin(2.0 * PI * k / 1024.0));
   for (int k = 0; k <= 1024; ++k) tw2048[k] = make_float2((float)std::cos(2.0 * PI * k / 2048.0), (float)-std::sin(2.0 * PI * k / 2048.0));
   float2 tw32[16];
@@ -315,16 +371,13 @@ int amt_frontend_create(int sr, int n_fft, int hop, int n_mels, double fmin, dou
   cudaError_t ce = cudaMemcpyToSymbol(c_tw32, tw32, sizeof(tw32));
   if (ce != cudaSuccess) { delete fe; return set_error(AMT_ERR_CUDA, "frontend: constant upload failed: %s", cudaGetErrorString(ce)); }
 
-  // one device blob
-  size_t o_win = 0, o_t1 = o_win + sizeof(float) * kNfft, o_t2 = o_t1 + sizeof(float2) * 1024,
-         o_st = o_t2 + sizeof(float2) * 1025 + 8, o_off = o_st + sizeof(int) * n_mels,
-         o_w = align_up(o_off + sizeof(int) * (n_mels + 1), 16), total = o_w + sizeof(float) * (w.size() + 1);
+  // one device blob: [tw1024 | tw2048 (+ pad) | fb_start | fb_w]  (fb_start and fb_w contiguous: one copy loop in the kernel)
+  const size_t o_t1 = 0, o_t2 = o_t1 + sizeof(float2) * 1024, o_st = align_up(o_t2 + sizeof(float2) * 1025, 16),
+               o_w = o_st + sizeof(int) * rounds * 32, total = o_w + sizeof(float) * w.size() + 16;
   std::vector<uint8_t> blob(total, 0);
-  memcpy(blob.data() + o_win, window.data(), sizeof(float) * kNfft);
   memcpy(blob.data() + o_t1, tw1024.data(), sizeof(float2) * 1024);
   memcpy(blob.data() + o_t2, tw2048.data(), sizeof(float2) * 1025);
-  memcpy(blob.data() + o_st, start.data(), sizeof(int) * n_mels);
-  memcpy(blob.data() + o_off, off.data(), sizeof(int) * (n_mels + 1));
+  memcpy(blob.data() + o_st, start.data(), sizeof(int) * rounds * 32);
   if (!w.empty()) memcpy(blob.data() + o_w, w.data(), sizeof(float) * w.size());
   void* d = nullptr;
   ce = cudaMalloc(&d, total);
@@ -332,14 +385,13 @@ int amt_frontend_create(int sr, int n_fft, int hop, int n_mels, double fmin, dou
   if (ce != cudaSuccess) { if (d) cudaFree(d); delete fe; return set_error(AMT_ERR_CUDA, "frontend: table upload failed: %s", cudaGetErrorString(ce)); }
   uint8_t* db = static_cast<uint8_t*>(d);
   fe->dev_blob = d;
-  fe->dev.window = reinterpret_cast<const float*>(db + o_win);
   fe->dev.tw1024 = reinterpret_cast<const float2*>(db + o_t1);
   fe->dev.tw2048 = reinterpret_cast<const float2*>(db + o_t2);
   fe->dev.fb_start = reinterpret_cast<const int*>(db + o_st);
-  fe->dev.fb_off = reinterpret_cast<const int*>(db + o_off);
   fe->dev.fb_w = reinterpret_cast<const float*>(db + o_w);
   fe->dev.n_mels = n_mels;
-  fe->dev.fb_nnz = static_cast<int>(w.size());
+  fe->dev.rounds = rounds;
+  fe->dev.fb_rows = fb_rows;
   fe->dev.hop = hop;
   *out = fe;
   return 0;
@@ -373,8 +425,9 @@ int amt_logmel_f32(amt_frontend* fe, const float* wav, int B, int n_samples, int
   const int T = 1 + n_samples / fe->hop;
   const int span = (kFramesPerCta - 1) * fe->hop + kNfft;
   const size_t smem = sizeof(float) * ((span + 3) & ~3) + sizeof(float2) * kWarpsPerCta * 32 * 33 +
-                      sizeof(float) * fe->n_mels * kFramesPerCta + sizeof(int) * (2 * fe->n_mels + 1) +
-                      sizeof(float) * fe->dev.fb_nnz;
+                      sizeof(float) * fe->dev.rounds * 32 * (kFramesPerCta + 1) + sizeof(int) * fe->dev.rounds * 32 +
+                      sizeof(float) * fe->dev.fb_rows * 32;
+  AMT_REQUIRE(smem <= 227 * 1024, "logmel: filterbank (n_mels %d) does not fit shared memory", fe->n_mels);
   AMT_FUNC_ATTR(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   fill_kernel<<<ceil_div(B, 256), 256, 0, stream>>>(chunk_max, B, -INFINITY);
   AMT_CHECK_LAUNCH();

@@ -18,7 +18,9 @@ size_t lstm_scratch_bytes(const amt_lstm_seq* seqs, int n_seq, int B);
 int run_attention(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip, cudaStream_t stream);
 int run_attention_tc(const void* qkv, void* out, int B, int T, int heads, int head_dim, float clip, cudaStream_t stream);
 // split != 0 (precise mode): outputs in the split-bf16 layout [hi | lo | hi (| 0)] per channel group
-int run_conv1(const float* x, const float* w, const float* bias, void* out, int B, int Fin, int T, int split, cudaStream_t stream);
+// chunk_max != nullptr: x is the unfloored log-mel; max(x, chunk_max[b] - top_db) is applied on load
+int run_conv1(const float* x, const float* chunk_max, float top_db, const float* w, const float* bias, void* out, int B, int Fin,
+              int T, int split, cudaStream_t stream);
 int run_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, void* out, long long rows,
                       int D, float eps, int split, cudaStream_t stream);
 int run_split3(const void* x, int in_f32, void* out, long long rows, int K, cudaStream_t stream);

@@ -217,8 +217,8 @@ static int conv(const amt_model& m, const void* X, int C, const void* X2, int C2
   return run_conv_halo(X, C, X2, C2, B, T, F, W, bias, N, kf, kt, out, 1, pool, m.KM > 1, s);
 }
 
-static int forward(amt_model& m, const float* logmel, int B, int T, float* frame, float* onset, float* offset,
-                   void* ws, cudaStream_t s) {
+static int forward(amt_model& m, const float* logmel, const float* chunk_max, float top_db, int B, int T, float* frame,
+                   float* onset, float* offset, void* ws, cudaStream_t s) {
   const amt_model_config& c = m.cfg;
   const bool large = c.kind == AMT_MODEL_CNN_RNN_LARGE;
   const bool precise = m.KM > 1;
@@ -236,7 +236,7 @@ static int forward(amt_model& m, const float* logmel, int B, int T, float* frame
   } while (0)
 
   // ---- CNN ----  (precise: every activation tensor carries km = 3 x the channels, [hi | lo | hi] per pixel)
-  STAGE("conv1", run_conv1(logmel, F_(m, "conv1.w"), F_(m, "conv1.b"), b.act1, B, c.n_mels, T, precise, s));
+  STAGE("conv1", run_conv1(logmel, chunk_max, top_db, F_(m, "conv1.w"), F_(m, "conv1.b"), b.act1, B, c.n_mels, T, precise, s));
   if (large) {
     STAGE("res1.c1", conv(m, b.act1, m.C1, nullptr, 0, B, T, m.F1, T_(m, "res1.c1.w"), F_(m, "res1.c1.b"), 64, 3, 3, b.h1, 0, s));
     STAGE("res1.c2", conv(m, b.h1, 64 * km, b.act1, m.C1, B, T, m.F1, T_(m, "res1.c2.w"), F_(m, "res1.c2.b"), 64, 3, 3, b.act2, 1, s));
@@ -517,8 +517,14 @@ size_t amt_model_workspace_bytes(const amt_model* m, int B, int T) {
 
 int amt_model_forward(amt_model* m, const float* logmel, int B, int T, float* frame, float* onset, float* offset,
                       void* workspace, size_t workspace_bytes, amt_stream_t stream) {
+  return amt_model_forward_db(m, logmel, nullptr, 0.0f, B, T, frame, onset, offset, workspace, workspace_bytes, stream);
+}
+
+int amt_model_forward_db(amt_model* m, const float* logmel, const float* chunk_max, float top_db, int B, int T, float* frame,
+                         float* onset, float* offset, void* workspace, size_t workspace_bytes, amt_stream_t stream) {
   using namespace amt;
   AMT_REQUIRE(m && logmel && frame && workspace, "model_forward: NULL argument");
+  AMT_REQUIRE(chunk_max == nullptr || top_db >= 0.0f, "model_forward: top_db must be >= 0 when chunk_max is given");
   AMT_REQUIRE(B >= 1 && T >= 1, "model_forward: B and T must be >= 1 (the reference's conv rejects T == 0 too)");
   if (!m->finalized) return set_error(AMT_ERR_STATE, "model_forward: call amt_model_finalize first");
   AMT_TRY(ensure_device());
@@ -526,7 +532,7 @@ int amt_model_forward(amt_model* m, const float* logmel, int B, int T, float* fr
   const size_t need = amt_model_workspace_bytes(m, B, T);
   if (workspace_bytes < need) return set_error(AMT_ERR_WORKSPACE, "model_forward: workspace %zu < %zu bytes", workspace_bytes, need);
   AMT_REQUIRE(static_cast<long long>(B) * T < (1ll << 30), "model_forward: B*T too large");
-  return forward(*m, logmel, B, T, frame, onset, offset, workspace, static_cast<cudaStream_t>(stream));
+  return forward(*m, logmel, chunk_max, top_db, B, T, frame, onset, offset, workspace, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

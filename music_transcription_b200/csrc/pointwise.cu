@@ -29,16 +29,19 @@ __device__ __forceinline__ uint32_t pack_bf16_lo(float x0, float x1, uint32_t hi
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                    int Fin, int T, int Fout) {
+                                                    int Fin, int T, int Fout, const float* __restrict__ chunk_max,
+                                                    float top_db) {
   constexpr int CS = SPLIT ? 128 : 32;             // channel stride of one output pixel
   __shared__ float tile[kC1Rows][kC1Pitch];
   const int tid = threadIdx.x;
   const int t0 = blockIdx.x * kC1T, fo0 = blockIdx.y * kC1F, b = blockIdx.z;
   const float* xb = x + static_cast<size_t>(b) * Fin * T;
+  // power_to_db's per-chunk floor (max - top_db, reference main.py:125) applied on load when the frontend left it to us
+  const float floor_v = chunk_max ? __ldg(chunk_max + b) - top_db : -INFINITY;
   for (int i = tid; i < kC1Rows * (kC1T + 2); i += 256) {
     const int rr = i / (kC1T + 2), cc = i - rr * (kC1T + 2);
     const int f = 2 * fo0 - 1 + rr, t = t0 - 1 + cc;
-    tile[rr][cc] = (f >= 0 && f < Fin && t >= 0 && t < T) ? __ldg(xb + static_cast<size_t>(f) * T + t) : 0.0f;
+    tile[rr][cc] = (f >= 0 && f < Fin && t >= 0 && t < T) ? fmaxf(__ldg(xb + static_cast<size_t>(f) * T + t), floor_v) : 0.0f;
   }
   const int lane = tid & 31, warp = tid >> 5;
   const int cg = lane & 7;                         // channels 4*cg .. 4*cg+3
@@ -93,13 +96,13 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x,
   }
 }
 
-int run_conv1(const float* x, const float* w, const float* bias, void* out, int B, int Fin, int T, int split,
-              cudaStream_t stream) {
+int run_conv1(const float* x, const float* chunk_max, float top_db, const float* w, const float* bias, void* out, int B, int Fin,
+              int T, int split, cudaStream_t stream) {
   const int Fout = Fin / 2;
   AMT_REQUIRE(Fout >= 1 && T >= 1 && B >= 1 && B <= 65535, "conv1: bad sizes");
   dim3 grid(ceil_div(T, kC1T), ceil_div(Fout, kC1F), B);
-  if (split) conv1_kernel<true><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout);
-  else conv1_kernel<false><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout);
+  if (split) conv1_kernel<true><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout, chunk_max, top_db);
+  else conv1_kernel<false><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout, chunk_max, top_db);
   AMT_CHECK_LAUNCH();
   return 0;
 }

@@ -37,6 +37,29 @@ CHUNK_LENGTH = 30.0
 THRESHOLD = 0.5
 
 
+class DeferredLogMel:
+    """What ``Frontend.logmel(..., defer_floor=True)`` returns: the dB spectrogram BEFORE power_to_db's per-chunk floor
+    (reference main.py:125, ``max - top_db``) plus the per-chunk maxima.  ``TranscriptionModel.forward`` accepts it in
+    place of the tensor and applies the floor inside its stem convolution's load (amt_model_forward_db) -- bitwise the
+    result of flooring first, without reading and re-writing the 1.2 MB per chunk once more.  ``floored()`` gives the
+    tensor the reference's ``audio_to_mel`` would have produced."""
+    __slots__ = ("mel", "chunk_max", "top_db")
+
+    def __init__(self, mel: torch.Tensor, chunk_max: torch.Tensor, top_db: float):
+        self.mel, self.chunk_max, self.top_db = mel, chunk_max, float(top_db)
+
+    @property
+    def shape(self):
+        return self.mel.shape
+
+    @property
+    def device(self):
+        return self.mel.device
+
+    def floored(self) -> torch.Tensor:
+        return torch.maximum(self.mel, (self.chunk_max - self.top_db).view(-1, 1, 1, 1))
+
+
 class Frontend:
     """Log-mel frontend handle (filterbank + FFT tables resident on one device)."""
 
@@ -76,8 +99,10 @@ class Frontend:
         _lib.check(_lib.lib().amt_frontend_filterbank_host(self._h, fb.ctypes.data))
         return fb
 
-    def logmel(self, wav: torch.Tensor, top_db: float = 80.0) -> torch.Tensor:
-        """wav (B, n_samples) float32 CUDA -> (B, 1, n_mels, T) float32 dB, floor at per-chunk max - top_db."""
+    def logmel(self, wav: torch.Tensor, top_db: float = 80.0, defer_floor: bool = False):
+        """wav (B, n_samples) float32 CUDA -> (B, 1, n_mels, T) float32 dB, floor at per-chunk max - top_db.
+        ``defer_floor``: return a ``DeferredLogMel`` (unfloored dB + per-chunk maxima) for ``TranscriptionModel.forward``
+        to floor while it loads its input -- the fused audio -> notes paths use this."""
         _lib.require_cuda(wav, "Frontend.logmel input")
         if wav.dim() == 1:
             wav = wav[None]
@@ -89,10 +114,11 @@ class Frontend:
         out = torch.empty(B, 1, self.n_mels, T, dtype=torch.float32, device=wav.device)
         cmax = torch.empty(B, dtype=torch.float32, device=wav.device)
         with torch.cuda.device(wav.device):
+            defer = defer_floor and top_db is not None
             _lib.check(_lib.lib().amt_logmel_f32(self._h, _lib.ptr(wav), B, n, wav.stride(0), _lib.ptr(out),
-                                                 float(top_db if top_db is not None else -1.0), _lib.ptr(cmax),
+                                                 float(top_db if (top_db is not None and not defer) else -1.0), _lib.ptr(cmax),
                                                  _lib.stream_ptr(wav.device)))
-        return out
+        return DeferredLogMel(out, cmax, top_db) if defer else out
 
 
 def audio_to_mel(audio_chunk, sr=SR, n_mels=N_MELS, hop_length=HOP_LENGTH, device=None):
@@ -258,7 +284,7 @@ def transcribe_chunks(model, wav: torch.Tensor, threshold: float = THRESHOLD, sr
     probs = torch.empty(n, 88, T, dtype=torch.float32, device=wav.device)
     L = _lib.lib()
     for i in range(0, n, batch):
-        mel = fe.logmel(wav[i:i + batch])
+        mel = fe.logmel(wav[i:i + batch], defer_floor=True)
         logits = model(mel)
         with torch.cuda.device(wav.device):
             _lib.check(L.amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), 0.0, _lib.ptr(probs[i:i + batch]), 0,
@@ -387,7 +413,7 @@ class StreamingTranscriber:
             sp = compute.cuda_stream
             if s.pcm is not None:
                 _lib.check(L.amt_pcm16_to_mono_f32(_lib.ptr(s.pcm), n * self.n_samples, 1, _lib.ptr(s.wav), sp))
-            mel = self.fe.logmel(s.wav[:n])
+            mel = self.fe.logmel(s.wav[:n], defer_floor=True)
             logits = self.model(mel)
             if self.roll_format == "f32":
                 _lib.check(L.amt_sigmoid_threshold(_lib.ptr(logits), logits.numel(), self.thr, _lib.ptr(s.probs), _lib.ptr(s.roll), sp))

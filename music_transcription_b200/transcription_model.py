@@ -213,7 +213,12 @@ class TranscriptionModel(nn.Module):
     def forward(self, x, return_all_heads=False, **kwargs):
         """x: (B, 1, n_mels, T) float32 CUDA -> logits (B, 88, T), or a dict with 'frame',
         'onset', 'offset' for the large model with heads when ``return_all_heads``
-        (reference transcription_model.py:105-108, cnn_rnn_model.py:337-345)."""
+        (reference transcription_model.py:105-108, cnn_rnn_model.py:337-345).
+        ``x`` may also be a ``pipeline.DeferredLogMel`` (unfloored dB + per-chunk maxima): the top_db floor is then applied
+        by the stem convolution's load -- the same values, one pass over the spectrogram less."""
+        chunk_max, top_db = None, 0.0
+        if hasattr(x, "chunk_max") and hasattr(x, "mel"):
+            chunk_max, top_db, x = x.chunk_max, float(x.top_db), x.mel
         if self.training and not self._warned_training:
             import warnings
             warnings.warn("TranscriptionModel (B200): forward always computes the EVAL-mode function (BatchNorm running statistics "
@@ -237,10 +242,13 @@ class TranscriptionModel(nn.Module):
             outs = torch.empty(n_out, B, 88, T, dtype=torch.float32, device=dev)
             need = L.amt_model_workspace_bytes(self._handle, B, T)
             ws_ptr, ws_bytes = self._workspace_for(need, dev)
-            _lib.check(L.amt_model_forward(self._handle, _lib.ptr(x), B, T, _lib.ptr(outs[0]),
-                                           _lib.ptr(outs[1]) if n_out == 3 else 0,
-                                           _lib.ptr(outs[2]) if n_out == 3 else 0,
-                                           ws_ptr, ws_bytes, _lib.stream_ptr(dev)))
+            if chunk_max is not None:
+                if chunk_max.device != dev or chunk_max.dtype != torch.float32 or chunk_max.numel() != B or not chunk_max.is_contiguous():
+                    raise ValueError("DeferredLogMel.chunk_max must be a contiguous float32 tensor of B values on the input's device")
+            _lib.check(L.amt_model_forward_db(self._handle, _lib.ptr(x), _lib.ptr(chunk_max), top_db, B, T, _lib.ptr(outs[0]),
+                                              _lib.ptr(outs[1]) if n_out == 3 else 0,
+                                              _lib.ptr(outs[2]) if n_out == 3 else 0,
+                                              ws_ptr, ws_bytes, _lib.stream_ptr(dev)))
         if n_out == 3:
             return {"frame": outs[0], "onset": outs[1], "offset": outs[2]}
         return outs[0]

@@ -79,6 +79,27 @@ def test_logmel_full_chunk_batch_shapes_and_floor():
     assert d.max() < LOGMEL_MAX_DB and d.mean() < LOGMEL_MEAN_DB, (d.max(), d.mean())
 
 
+def test_deferred_floor_is_bitwise_the_floored_path():
+    """Frontend.logmel(defer_floor=True) + amt_model_forward_db (the floor max(x, chunk max - 80 dB) applied by the stem
+    convolution's load) must give bit for bit what flooring first gives -- incl. chunks where the floor bites hard (half of
+    the chunk digital silence: -100 dB cells against a +20 dB maximum) and n_mels / batch shapes off the tile sizes."""
+    fe = pipeline.Frontend.get(device=DEV)
+    wav = torch.from_numpy(synth.piano_chord_batch([3, 4, 5], n_samples=64000)).to(DEV)
+    wav[1, 20000:] = 0.0                               # floor active on most of this chunk
+    wav[2] *= 1e-4                                     # a quiet chunk: its own maximum sets its floor
+    mel = fe.logmel(wav)
+    d = fe.logmel(wav, defer_floor=True)
+    assert isinstance(d, pipeline.DeferredLogMel) and d.shape == mel.shape
+    assert torch.equal(d.floored(), mel)
+    assert float((d.mel < mel).float().mean()) > 0.05  # the deferred tensor really is unfloored
+    for mt in ("cnn_rnn", "cnn_rnn_large"):
+        m = TranscriptionModel(model_type=mt, n_mels=320, hidden_size=128, num_layers=1, device=DEV).eval()
+        m.load_state_dict(synth.synth_state_dict(mt, 320, 128, 1, seed=2))
+        assert torch.equal(m(d), m(mel)), mt
+    with pytest.raises(ValueError):
+        m(pipeline.DeferredLogMel(d.mel, d.chunk_max[:2], 80.0))
+
+
 def _load_case(path):
     g = np.load(path)
     n_mels, H, L, B, T, attn, heads, seed, xseed = [int(v) for v in g["cfg"]]
