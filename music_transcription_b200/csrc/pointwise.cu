@@ -1,6 +1,7 @@
 // HBM-bound kernels around the GEMMs: the Cin=1 stem convolution, residual+LayerNorm,
 // head finalisation (transpose to (B,88,T)) and sigmoid/threshold.
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -26,6 +27,32 @@ __device__ __forceinline__ uint32_t pack_bf16_lo(float x0, float x1, uint32_t hi
   return ptx::pack_bf16(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
 }
 
+// Stage the CTA's input tile (rows 2 fo0 - 1 .., frames t0 - 1 ..; zero outside the spectrogram = the conv padding) with
+// ALL of a thread's loads in flight before the first use: a load -> floor -> store loop pays one DRAM round trip per
+// element (ncu: 40 % of the kernel's stall samples sat on that dependency), 18 times per thread.
+constexpr int kC1Fill = (kC1Rows * (kC1T + 2) + 255) / 256;
+template <typename Store>
+__device__ __forceinline__ void conv1_fill_tile(const float* __restrict__ xb, int Fin, int T, int fo0, int t0, float floor_v, int tid,
+                                                Store store) {
+  float v[kC1Fill];
+  uint32_t ok = 0;
+#pragma unroll
+  for (int u = 0; u < kC1Fill; ++u) {
+    const int i = tid + u * 256;
+    const int rr = i / (kC1T + 2), cc = i - rr * (kC1T + 2);
+    const int f = 2 * fo0 - 1 + rr, t = t0 - 1 + cc;
+    const bool in = rr < kC1Rows && f >= 0 && f < Fin && t >= 0 && t < T;
+    v[u] = in ? __ldg(xb + static_cast<size_t>(f) * T + t) : 0.0f;
+    ok |= static_cast<uint32_t>(in) << u;
+  }
+#pragma unroll
+  for (int u = 0; u < kC1Fill; ++u) {
+    const int i = tid + u * 256;
+    const int rr = i / (kC1T + 2), cc = i - rr * (kC1T + 2);
+    if (rr < kC1Rows) store(rr, cc, ((ok >> u) & 1u) ? fmaxf(v[u], floor_v) : 0.0f);
+  }
+}
+
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
@@ -38,11 +65,7 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x,
   const float* xb = x + static_cast<size_t>(b) * Fin * T;
   // power_to_db's per-chunk floor (max - top_db, reference main.py:125) applied on load when the frontend left it to us
   const float floor_v = chunk_max ? __ldg(chunk_max + b) - top_db : -INFINITY;
-  for (int i = tid; i < kC1Rows * (kC1T + 2); i += 256) {
-    const int rr = i / (kC1T + 2), cc = i - rr * (kC1T + 2);
-    const int f = 2 * fo0 - 1 + rr, t = t0 - 1 + cc;
-    tile[rr][cc] = (f >= 0 && f < Fin && t >= 0 && t < T) ? fmaxf(__ldg(xb + static_cast<size_t>(f) * T + t), floor_v) : 0.0f;
-  }
+  conv1_fill_tile(xb, Fin, T, fo0, t0, floor_v, tid, [&](int rr, int cc, float v) { tile[rr][cc] = v; });
   const int lane = tid & 31, warp = tid >> 5;
   const int cg = lane & 7;                         // channels 4*cg .. 4*cg+3
   const int fl = warp * 4 + (lane >> 3);           // pooled bin inside the CTA tile
@@ -96,13 +119,120 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x,
   }
 }
 
+// ----------------------------------------------------------------------------
+// conv1 on the tensor pipe (fast mode).  The FFMA stencil above is bound by the fp32 pipe (72 FMAs per thread and
+// frame: 0.36-0.42 ms for 60 chunks, 2.3x its 64-byte-per-pixel write floor).  K = 9 is not a tensor-core shape, but
+// 27 is: with x = hi + lo and w = wh + wl (bf16 pairs, |residual| < 2^-17 |x|) the stencil becomes a K = 27 (padded
+// to 32) contraction  sum_tap (hi wh + lo wh + hi wl)  with fp32 accumulation -- three bf16 products per tap, exact
+// to ~2^-16 relative like the split-bf16 operands of the precise mode.  mma.sync m16n8k16 (the warp-level path: a
+// 16-frame x 32-channel tile per warp is far below a tcgen05 tile): M = 16 consecutive frames of one frequency row,
+// N = 32 channels = 4 n-tiles, K = 2 k-steps.
+//   * The input tile is staged ONCE as packed words (hi | lo << 16).  K slot pairs are laid out so that every A
+//     register is one such word: thread (g = lane / 4, c = lane % 4) owns taps c and c + 4 --
+//       k-step 0: slots (2c, 2c+1)   = tap c   (hi, lo) x (wh, wh);   slots (2c+8, 2c+9)   = tap c+4 (hi, lo) x (wh, wh)
+//       k-step 1: slots (16+2c, 17+2c) = (hi[c], hi[c+4]) x (wl[c], wl[c+4])  -- one PRMT of the two words it holds;
+//                 slots (24+2c, 25+2c) = tap 8 (hi, lo) x (wh, wh) for c = 0, x (wl, 0) for c = 1, x 0 otherwise
+//     so a fragment costs 3 shared-memory loads per frame row (taps c, c+4, 8) for 8 MMAs.
+//   * The weight fragments (16 registers) are built once per thread from the fp32 folded weights.
+//   * Both pre-pool rows of a pooled bin are accumulated by the same thread (bias in the accumulator init), so
+//     ReLU(max(.,.)) is register math; each quad then writes a pixel's 64 channel bytes.
+// ----------------------------------------------------------------------------
+constexpr int kC1P = 76;     // tile pitch in words: rows 0/1/2 of a fragment's taps fall into disjoint banks
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t split_word(float x) {      // bf16(x) | bf16(x - bf16(x)) << 16
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  return static_cast<uint32_t>(__bfloat16_as_ushort(h)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l)) << 16);
+}
+
+__global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int Fin,
+                                                        int T, int Fout, const float* __restrict__ chunk_max, float top_db) {
+  __shared__ uint32_t tile[kC1Rows * kC1P];
+  const int tid = threadIdx.x;
+  const int t0 = blockIdx.x * kC1T, fo0 = blockIdx.y * kC1F, b = blockIdx.z;
+  const float* xb = x + static_cast<size_t>(b) * Fin * T;
+  const float floor_v = chunk_max ? __ldg(chunk_max + b) - top_db : -INFINITY;
+  conv1_fill_tile(xb, Fin, T, fo0, t0, floor_v, tid, [&](int rr, int cc, float v) { tile[rr * kC1P + cc] = split_word(v); });
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  // weight fragments: n-tile j covers channels 8j .. 8j+7, this thread's column is channel 8j + g
+  uint32_t wb[4][4];                               // [j][k-step 0: b0, b1 | k-step 1: b0, b1]
+  float bs[4][2];                                  // bias of this thread's accumulator columns: channels 8j + 2c, + 1
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float* wr = w + (8 * j + g) * 9;
+    const uint32_t s0 = split_word(__ldg(wr + c)), s1 = split_word(__ldg(wr + c + 4)), s8 = split_word(__ldg(wr + 8));
+    wb[j][0] = __byte_perm(s0, s0, 0x1010);        // (wh[c], wh[c])
+    wb[j][1] = __byte_perm(s1, s1, 0x1010);        // (wh[c+4], wh[c+4])
+    wb[j][2] = __byte_perm(s0, s1, 0x7632);        // (wl[c], wl[c+4])
+    wb[j][3] = c == 0 ? __byte_perm(s8, s8, 0x1010) : (c == 1 ? (s8 >> 16) : 0u);   // (wh[8], wh[8]) | (wl[8], 0) | 0
+    bs[j][0] = __ldg(bias + 8 * j + 2 * c);
+    bs[j][1] = __ldg(bias + 8 * j + 2 * c + 1);
+  }
+  __syncthreads();
+  const int offA = (c / 3) * kC1P + (c % 3);                       // tap c      = (kf, kt) = (c / 3, c % 3)
+  const int offB = ((c + 4) / 3) * kC1P + ((c + 4) % 3);           // tap c + 4
+  const int off8 = 2 * kC1P + 2;                                   // tap 8
+#pragma unroll 1
+  for (int bi = 0; bi < 4; ++bi) {
+    const int fl = warp * 4 + bi;                                  // pooled bin inside the CTA tile
+    const int fo = fo0 + fl;
+    if (fo >= Fout) break;
+#pragma unroll 1
+    for (int mt = 0; mt < kC1T / 16; ++mt) {
+      if (t0 + 16 * mt >= T) break;
+      float acc[2][4][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[r][j][0] = acc[r][j][2] = bs[j][0];
+          acc[r][j][1] = acc[r][j][3] = bs[j][1];
+        }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {                                // the two pre-pool rows 2 fo, 2 fo + 1
+        const uint32_t* p0 = tile + (2 * fl + r) * kC1P + 16 * mt + g;
+        const uint32_t a_lo = p0[offA], a_hi = p0[offA + 8];       // tap c:   frames g, g + 8
+        const uint32_t b_lo = p0[offB], b_hi = p0[offB + 8];       // tap c+4
+        const uint32_t e_lo = p0[off8], e_hi = p0[off8 + 8];       // tap 8
+        const uint32_t m_lo = __byte_perm(a_lo, b_lo, 0x5410), m_hi = __byte_perm(a_hi, b_hi, 0x5410);   // (hi[c], hi[c+4])
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mma_bf16_16816(acc[r][j], a_lo, a_hi, b_lo, b_hi, wb[j][0], wb[j][1]);
+          mma_bf16_16816(acc[r][j], m_lo, m_hi, e_lo, e_hi, wb[j][2], wb[j][3]);
+        }
+      }
+      // ReLU(max over the pooled pair) -> bf16 pairs; rows g and g + 8 of the frame tile
+      const int ta = t0 + 16 * mt + g, tb = ta + 8;
+      __nv_bfloat16* oa = out + ((static_cast<size_t>(b) * T + ta) * Fout + fo) * 32 + 2 * c;
+      __nv_bfloat16* ob = oa + static_cast<size_t>(8) * Fout * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t va = ptx::pack_bf16(fmaxf(fmaxf(acc[0][j][0], acc[1][j][0]), 0.0f), fmaxf(fmaxf(acc[0][j][1], acc[1][j][1]), 0.0f));
+        const uint32_t vb = ptx::pack_bf16(fmaxf(fmaxf(acc[0][j][2], acc[1][j][2]), 0.0f), fmaxf(fmaxf(acc[0][j][3], acc[1][j][3]), 0.0f));
+        if (ta < T) *reinterpret_cast<uint32_t*>(oa + 8 * j) = va;
+        if (tb < T) *reinterpret_cast<uint32_t*>(ob + 8 * j) = vb;
+      }
+    }
+  }
+}
+
 int run_conv1(const float* x, const float* chunk_max, float top_db, const float* w, const float* bias, void* out, int B, int Fin,
               int T, int split, cudaStream_t stream) {
   const int Fout = Fin / 2;
   AMT_REQUIRE(Fout >= 1 && T >= 1 && B >= 1 && B <= 65535, "conv1: bad sizes");
   dim3 grid(ceil_div(T, kC1T), ceil_div(Fout, kC1F), B);
+  static const bool force_ffma = getenv("AMT_CONV1_FFMA") != nullptr;       // bring-up switch: the fp32 stencil in fast mode too
   if (split) conv1_kernel<true><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout, chunk_max, top_db);
-  else conv1_kernel<false><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout, chunk_max, top_db);
+  else if (force_ffma) conv1_kernel<false><<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout, chunk_max, top_db);
+  else conv1_mma_kernel<<<grid, 256, 0, stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), Fin, T, Fout, chunk_max, top_db);
   AMT_CHECK_LAUNCH();
   return 0;
 }

@@ -49,7 +49,17 @@ def emu_forward(P, x, model_type, n_mels, H, layers, use_attention=True, use_hea
     large = model_type.lower() in ("cnn_rnn_large", "large")
     B, _, _, T = x.shape
     R = lambda t: _r(t, bf16_acts)
-    y = F.conv2d(x, P["conv1.w"].view(32, 1, 3, 3), P["conv1.b"], padding=1).relu()
+    # stem conv as conv1_mma_kernel computes it (fast mode): x = hi + lo, w = wh + wl in bf16, the three products
+    # hi*wh + lo*wh + hi*wl accumulated in fp32 (the fp32 stencil of the precise mode agrees with it to 2^-16)
+    w1 = P["conv1.w"].view(32, 1, 3, 3).float()
+    if bf16_acts:
+        sp = lambda t: (t.to(torch.bfloat16).float(), (t - t.to(torch.bfloat16).float()).to(torch.bfloat16).float())
+        (xh, xl), (wh, wl) = sp(x.float()), sp(w1)
+        y = (F.conv2d(xh.double(), wh.double(), padding=1) + F.conv2d(xl.double(), wh.double(), padding=1)
+             + F.conv2d(xh.double(), wl.double(), padding=1)).float() + P["conv1.b"].view(1, 32, 1, 1)
+        y = y.relu()
+    else:
+        y = F.conv2d(x, w1, P["conv1.b"], padding=1).relu()
     y = F.max_pool2d(y, (2, 1)).permute(0, 3, 2, 1)                       # [B,T,F1,32]
     act1 = R(y.contiguous())                                              # 32 channels
     if large:

@@ -100,6 +100,35 @@ def test_deferred_floor_is_bitwise_the_floored_path():
         m(pipeline.DeferredLogMel(d.mel, d.chunk_max[:2], 80.0))
 
 
+@pytest.mark.parametrize("n_mels,T,B", [(320, 938, 2), (37, 70, 3), (64, 129, 1)])
+def test_stem_conv_tensor_path_matches_fp32_conv(n_mels, T, B):
+    """conv1 (Conv 1->32 3x3 + folded BN + ReLU + MaxPool(2,1), reference cnn_rnn_model.py:179-182) runs on the tensor
+    pipe in fast mode as a K = 27 split-bf16 contraction (pointwise.cu).  Its bf16 output, read back from the workspace,
+    must be the exact convolution rounded to bf16: at most one bf16 ulp apart, and exactly equal for most
+    elements.  Shapes off the 64-frame / 32-bin tile included; log-mel-like magnitudes (tens of dB)."""
+    import torch.nn.functional as F
+    mt = "cnn_rnn"
+    sd = synth.synth_state_dict(mt, n_mels, 128, 1, seed=4)
+    m = TranscriptionModel(model_type=mt, n_mels=n_mels, hidden_size=128, num_layers=1, device=DEV).eval()
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(n_mels + T)
+    x = (torch.randn(B, 1, n_mels, T, generator=g) * 20.0 - 10.0).to(DEV)
+    m(x)
+    F1 = n_mels // 2
+    got = m.workspace_tensor("act1", B, T, torch.bfloat16, F1 * 32).float().view(B, T, F1, 32)
+    w = m.packed_tensor("conv1.w", torch.float32).view(32, 1, 3, 3)
+    bias = m.packed_tensor("conv1.b", torch.float32)
+    ref = F.max_pool2d(F.conv2d(x.double(), w.double(), bias.double(), padding=1).relu(), (2, 1))     # (B, 32, F1, T)
+    ref = ref.permute(0, 3, 2, 1).float()
+    # size of the terms that were summed (the split-bf16 contraction is exact to 2^-16 of THAT, not of the result)
+    mag = F.max_pool2d(F.conv2d(x.double().abs(), w.double().abs(), bias.double().abs(), padding=1), (2, 1)).permute(0, 3, 2, 1).float()
+    err = (got - ref).abs()
+    tol = ref.abs() * 2.0 ** -7 + mag * 2.0 ** -14      # one bf16 ulp of the value (2^-8 .. 2^-7) + the contraction's own error
+    assert bool((err <= tol).all()), float((err / tol).max())
+    exact = (got == ref.to(torch.bfloat16).float()).float().mean().item()
+    assert exact > 0.85, exact                          # (a 2^-16 error flips a bf16 rounding in ~1 % x cancellation of the cases)
+
+
 def _load_case(path):
     g = np.load(path)
     n_mels, H, L, B, T, attn, heads, seed, xseed = [int(v) for v in g["cfg"]]
