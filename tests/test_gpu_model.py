@@ -173,7 +173,7 @@ def test_model_matches_reference_golden(path):
     assert pred.shape == g["pred"].shape and set(np.unique(pred.cpu().numpy())) <= {0.0, 1.0}
     flips = (pred.cpu().numpy() != g["pred"]).mean()
     _report(f"fast.{os.path.basename(path)[6:-4]}.pred", flips=flips)
-    assert flips < 0.02
+    assert flips < 0.009                          # stress checkpoints: measured 0.19-0.68 % (profiles/r2_parity.md)
 
 
 @pytest.mark.parametrize("mt,n_mels,H,L,attn,heads", [
