@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x,
 //     ReLU(max(.,.)) is register math; each quad then writes a pixel's 64 channel bytes.
 // ----------------------------------------------------------------------------
 constexpr int kC1P = 76;     // tile pitch in words: rows 0/1/2 of a fragment's taps fall into disjoint banks
+constexpr int kC1StagePitch = 20;   // words per staged output row (16 used): conflict-free fragment writes, 16-byte aligned rows
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                                uint32_t b1) {
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int Fin,
                                                         int T, int Fout, const float* __restrict__ chunk_max, float top_db) {
   __shared__ uint32_t tile[kC1Rows * kC1P];
+  __shared__ __align__(16) uint32_t stage[8 * 16 * kC1StagePitch];
   const int tid = threadIdx.x;
   const int t0 = blockIdx.x * kC1T, fo0 = blockIdx.y * kC1F, b = blockIdx.z;
   const float* xb = x + static_cast<size_t>(b) * Fin * T;
@@ -209,17 +211,25 @@ __global__ void __launch_bounds__(256) conv1_mma_kernel(const float* __restrict_
           mma_bf16_16816(acc[r][j], m_lo, m_hi, e_lo, e_hi, wb[j][2], wb[j][3]);
         }
       }
-      // ReLU(max over the pooled pair) -> bf16 pairs; rows g and g + 8 of the frame tile
-      const int ta = t0 + 16 * mt + g, tb = ta + 8;
-      __nv_bfloat16* oa = out + ((static_cast<size_t>(b) * T + ta) * Fout + fo) * 32 + 2 * c;
-      __nv_bfloat16* ob = oa + static_cast<size_t>(8) * Fout * 32;
+      // ReLU(max over the pooled pair) -> bf16 pairs, transposed through a warp-private staging tile so that a lane
+      // stores 16 contiguous bytes and a quad a pixel's whole 64-byte channel row (the fragment layout gives a lane
+      // 4 bytes of every 16: eight half-filled sectors per store instruction, ncu: l1tex 73 % from those)
+      uint32_t* stg = stage + warp * (16 * kC1StagePitch);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t va = ptx::pack_bf16(fmaxf(fmaxf(acc[0][j][0], acc[1][j][0]), 0.0f), fmaxf(fmaxf(acc[0][j][1], acc[1][j][1]), 0.0f));
-        const uint32_t vb = ptx::pack_bf16(fmaxf(fmaxf(acc[0][j][2], acc[1][j][2]), 0.0f), fmaxf(fmaxf(acc[0][j][3], acc[1][j][3]), 0.0f));
-        if (ta < T) *reinterpret_cast<uint32_t*>(oa + 8 * j) = va;
-        if (tb < T) *reinterpret_cast<uint32_t*>(ob + 8 * j) = vb;
+        stg[g * kC1StagePitch + 4 * j + c] =
+            ptx::pack_bf16(fmaxf(fmaxf(acc[0][j][0], acc[1][j][0]), 0.0f), fmaxf(fmaxf(acc[0][j][1], acc[1][j][1]), 0.0f));
+        stg[(g + 8) * kC1StagePitch + 4 * j + c] =
+            ptx::pack_bf16(fmaxf(fmaxf(acc[0][j][2], acc[1][j][2]), 0.0f), fmaxf(fmaxf(acc[0][j][3], acc[1][j][3]), 0.0f));
       }
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = g + 8 * h, tt = t0 + 16 * mt + row;       // lane (g, c): frame row, channels 8c .. 8c + 7
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + row * kC1StagePitch + 4 * c);
+        if (tt < T) *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * T + tt) * Fout + fo) * 32 + 8 * c) = v;
+      }
+      __syncwarp();
     }
   }
 }

@@ -65,6 +65,20 @@ def test_logmel_matches_oracle(case):
     assert d.max() < LOGMEL_MAX_DB and d.mean() < LOGMEL_MEAN_DB, (case, d.max(), d.mean())
 
 
+@pytest.mark.parametrize("n_mels", [229, 128, 64, 37, 512])
+def test_logmel_other_filterbank_sizes(n_mels):
+    """The reference class default is n_mels = 229 and checkpoints exist for other sizes: the ELL filterbank (rounds of 32
+    filters, the round as wide as its widest band) must hold for few wide filters (37: up to ~90 bins per band), a
+    partial last round (229, 37) and more filters than bins can separate (512: empty low filters)."""
+    from oracle import frontend as ofe
+    y = synth.piano_chord(7, n_samples=40000)
+    mel = pipeline.audio_to_mel(y, n_mels=n_mels, device=DEV)
+    ref = ofe.logmel(y, n_mels=n_mels)
+    assert mel.shape == (1, 1, n_mels, 1 + len(y) // 512)
+    d = np.abs(mel[0, 0].cpu().numpy() - ref)
+    assert d.max() < LOGMEL_MAX_DB and d.mean() < LOGMEL_MEAN_DB, (n_mels, d.max(), d.mean())
+
+
 def test_logmel_full_chunk_batch_shapes_and_floor():
     from oracle import frontend as ofe
     wav = torch.from_numpy(synth.piano_chord_batch([0, 1, 2])).to(DEV)
