@@ -188,6 +188,19 @@ int amt_threshold_notes(const float* vals, int n_seg, int n_pitch, int T, int64_
 int amt_bits_notes(const uint32_t* bits, int n_seg, int n_pitch, int T, int32_t* notes, int cap, int32_t* counts,
                    int32_t* scratch, size_t scratch_ints, amt_stream_t stream);
 
+/* Onset / offset-aware note decoding on bit-packed rolls of the three heads of CNNRNNModelLarge
+ * (reference models/cnn_rnn_model.py:333-345 computes them; its inference path, main.py:150-160, thresholds the frame
+ * head only and has no such decoder -- the rule is defined here and restated in oracle/notes.py).  frame_bits /
+ * onset_bits / offset_bits (offset_bits may be NULL): [n_seg][n_pitch][ceil(T/32)] from amt_pack_roll_u32, segments
+ * concatenated along time.  Per pitch: a rising edge of the onset head starts a note; it ends at the first later frame
+ * where neither frame nor onset head is active, the offset head is active, or another onset starts -- or at the end of
+ * the roll; sounding frames no onset opened are ignored.  Output and counts as amt_bits_notes.  scratch: device int32
+ * [amt_onset_notes_scratch_ints(n_pitch)].  n_pitch <= 1024.  Asynchronous. */
+size_t amt_onset_notes_scratch_ints(int n_pitch);
+int amt_onset_notes(const uint32_t* frame_bits, const uint32_t* onset_bits, const uint32_t* offset_bits, int n_seg,
+                    int n_pitch, int T, int32_t* notes, int cap, int32_t* counts, int32_t* scratch, size_t scratch_ints,
+                    amt_stream_t stream);
+
 /* Framewise TP/FP/FN of reference scripts/evaluate.py:524-553 for every piece
  * and every threshold in one pass.  probs/target: [n_pieces][n_pitch][T_stride]
  * f32, only the first lengths[i] frames of piece i count; thresholds: sorted

@@ -17,7 +17,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libamt_sm100.so")
-SOURCES = ["api.cu", "frontend.cu", "tc_gemm.cu", "conv_halo.cu", "lstm.cu", "attention.cu", "attention_tc.cu", "pointwise.cu", "notes.cu", "resample.cu", "loss.cu", "model.cu", "model_load.cu"]
+SOURCES = ["api.cu", "frontend.cu", "tc_gemm.cu", "conv_halo.cu", "lstm.cu", "attention.cu", "attention_tc.cu", "pointwise.cu", "notes.cu", "onset_notes.cu", "resample.cu", "loss.cu", "model.cu", "model_load.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

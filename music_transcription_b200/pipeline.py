@@ -243,6 +243,49 @@ def extract_notes_from_bits(bits: torch.Tensor, T: int, cap: int | None = None) 
     return notes[:total].cpu().numpy()
 
 
+def extract_notes_onset_aware(frame: torch.Tensor, onset: torch.Tensor, offset: torch.Tensor | None = None, threshold: float = THRESHOLD,
+                              onset_threshold: float = THRESHOLD, offset_threshold: float = THRESHOLD, logits: bool = True,
+                              cap: int | None = None) -> np.ndarray:
+    """Notes from the three heads of ``model(mel, return_all_heads=True)`` (the reference computes the
+    onset / offset heads, cnn_rnn_model.py:333-345, but its inference path never decodes them): ``frame`` / ``onset`` /
+    ``offset`` are (n_chunks, 88, T) CUDA tensors of logits (``logits=True``: sigmoid is applied) or probabilities; chunks
+    are concatenated along time like main.py:270-275.  A rising edge of ``sigmoid(onset) > onset_threshold`` starts a note;
+    it ends where frame and onset are both inactive, where the offset head fires, at the next onset, or at the end
+    (``amt_onset_notes``; rule restated in oracle/notes.py).  Returns int32 (n, 3) rows (pitch_idx, onset_frame,
+    offset_frame), pitch-major -- the rows ``NoteList`` / ``smf`` take."""
+    _lib.require_cuda(frame, "extract_notes_onset_aware input")
+    if frame.dim() == 2:
+        frame, onset = frame[None], onset[None]
+        offset = offset[None] if offset is not None else None
+    n, P, T = frame.shape
+    L = _lib.lib()
+    dev = frame.device
+    W = (T + 31) // 32
+    with torch.cuda.device(dev):
+        sp = _lib.stream_ptr(dev)
+        packed = []
+        for t, thr in ((frame, threshold), (onset, onset_threshold), (offset, offset_threshold)):
+            if t is None:
+                packed.append(None)
+                continue
+            if t.shape != frame.shape:
+                raise ValueError("extract_notes_onset_aware: the heads must have the same shape")
+            t = t.contiguous().float()
+            bits = torch.empty(n, P, W, dtype=torch.int32, device=dev)
+            _lib.check(L.amt_pack_roll_u32(_lib.ptr(t), n * P, T, float(thr), int(logits), _lib.ptr(bits), sp))
+            packed.append(bits)
+        cap = int(cap) if cap is not None else P * ((n * T + 1) // 2)
+        notes = torch.empty(max(cap, 1), 3, dtype=torch.int32, device=dev)
+        counts = torch.empty(P + 1, dtype=torch.int32, device=dev)
+        scratch = torch.empty(max(int(L.amt_onset_notes_scratch_ints(P)), 1), dtype=torch.int32, device=dev)
+        _lib.check(L.amt_onset_notes(_lib.ptr(packed[0]), _lib.ptr(packed[1]), _lib.ptr(packed[2]), n, P, T, _lib.ptr(notes), cap,
+                                     _lib.ptr(counts), _lib.ptr(scratch), scratch.numel(), sp))
+        total = int(counts[P].item())
+    if total > cap:
+        raise _lib.AmtError(f"extract_notes_onset_aware: {total} notes exceed cap {cap}")
+    return notes[:total].cpu().numpy()
+
+
 def pianoroll_to_midi(pianoroll, fs, min_midi=21) -> NoteList:
     """(88, T) roll (numpy or tensor, values {0,1}) -> notes, grouped on the GPU (main.py:204-223)."""
     roll = torch.as_tensor(np.ascontiguousarray(pianoroll, dtype=np.float32)) if not torch.is_tensor(pianoroll) else pianoroll

@@ -367,6 +367,48 @@ def test_bits_notes_equals_float_notes_incl_seams():
         assert np.array_equal(got, onotes.group_notes(roll))
 
 
+def _runs_roll(rng, P, N, p_on, p_off):
+    """A (P, N) {0,1} roll of random runs (two-state Markov chain): realistic note-like structure, incl. long notes."""
+    r = np.zeros((P, N), np.float32)
+    state = rng.random(P) < 0.3
+    for t in range(N):
+        flip = rng.random(P)
+        state = np.where(state, flip >= p_off, flip < p_on)
+        r[:, t] = state
+    return r
+
+
+@pytest.mark.parametrize("n_seg,T,with_offset", [(1, 938, True), (4, 938, True), (3, 70, False), (2, 1100, True), (5, 33, True), (1, 1, False)])
+def test_onset_aware_notes_are_bit_exact_with_the_oracle(n_seg, T, with_offset):
+    """amt_onset_notes (decoding of the frame + onset + offset heads) == oracle.notes.group_notes_onset_aware on
+    the concatenated rolls: notes crossing segment seams and 1024-frame block seams (T = 1100), T not a multiple of 32, dense
+    and sparse onsets, re-strikes inside a sounding note, frames no onset opened, notes still open at the end."""
+    from music_transcription_b200 import pipeline
+    from oracle import notes as onotes
+    rng = np.random.default_rng(1000 * n_seg + T)
+    P, N = 88, n_seg * T
+    frame = _runs_roll(rng, P, N, 0.02, 0.03)
+    onset = _runs_roll(rng, P, N, 0.03, 0.6)
+    offset = _runs_roll(rng, P, N, 0.01, 0.7) if with_offset else None
+    frame[5, :] = 1.0                                   # sounds through every seam; one onset at the very start
+    onset[5, :] = 0.0
+    onset[5, 0] = 1.0
+    if N > 40:
+        onset[6, :] = 0.0
+        frame[6, :] = 1.0
+        onset[6, N - 1] = 1.0                           # a note that starts on the last frame
+        onset[7, :] = 1.0                               # onset head stuck high: ONE rising edge
+    want = onotes.group_notes_onset_aware(frame, onset, offset)
+    seg = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a.reshape(P, n_seg, T).transpose(1, 0, 2))).to(DEV)
+    got = pipeline.extract_notes_onset_aware(seg(frame), seg(onset), seg(offset), 0.5, 0.5, 0.5, logits=False)
+    assert got.dtype == np.int32 and np.array_equal(got, want), (got.shape, want.shape)
+    if n_seg == 4:                                      # logits in, thresholds through the sigmoid, and a too-small cap
+        lg = lambda a: (seg(a) * 8.0 - 4.0)
+        assert np.array_equal(pipeline.extract_notes_onset_aware(lg(frame), lg(onset), lg(offset)), want)
+        with pytest.raises(_lib.AmtError):
+            pipeline.extract_notes_onset_aware(seg(frame), seg(onset), seg(offset), logits=False, cap=len(want) - 1)
+
+
 def test_async_roll_gather_single_process():
     from music_transcription_b200 import pipeline, sharding
     T, n = 70, 5

@@ -143,6 +143,24 @@ def test_stem_conv_tensor_path_matches_fp32_conv(n_mels, T, B):
     assert exact > 0.85, exact                          # (a 2^-16 error flips a bf16 rounding in ~1 % x cancellation of the cases)
 
 
+def test_three_heads_decode_to_notes_end_to_end():
+    """audio -> log-mel -> CNNRNNModelLarge (all heads) -> onset/offset-aware notes: the decoder sees the same thresholded
+    rolls the oracle sees (sigmoid and strict float32 compare on the GPU == numpy on the downloaded logits up to cells that
+    sit exactly on the threshold, which random-init logits do not), so the note lists must be equal."""
+    from oracle import notes as onotes
+    fe = pipeline.Frontend.get(device=DEV)
+    wav = torch.from_numpy(synth.piano_chord_batch([1, 2], n_samples=48000)).to(DEV)
+    m = TranscriptionModel("cnn_rnn_large", n_mels=320, hidden_size=128, num_layers=1, device=DEV).eval()
+    m.load_state_dict(synth.synth_state_dict("cnn_rnn_large", 320, 128, 1, seed=6))
+    heads = m(fe.logmel(wav, defer_floor=True), return_all_heads=True)
+    got = pipeline.extract_notes_onset_aware(heads["frame"], heads["onset"], heads["offset"], 0.5, 0.5, 0.5)
+    roll = lambda k: np.concatenate(list((torch.sigmoid(heads[k]).cpu().numpy() > np.float32(0.5)).astype(np.float32)), axis=1)
+    want = onotes.group_notes_onset_aware(roll("frame"), roll("onset"), roll("offset"))
+    assert len(want) > 0 and np.array_equal(got, want)
+    nl = pipeline.NoteList(got, fs=16000 / 512)
+    assert len(nl) == len(got)
+
+
 def _load_case(path):
     g = np.load(path)
     n_mels, H, L, B, T, attn, heads, seed, xseed = [int(v) for v in g["cfg"]]

@@ -85,6 +85,22 @@ def test_notes_oracle_matches_reference_pianoroll_to_midi():
     assert any(p == 5 and s == 930 and e == 945 for p, s, e in seam)        # merged across the chunk seam
 
 
+def test_onset_aware_decoding_rule_on_hand_cases():
+    """The onset / offset-aware decoder has no counterpart in the reference (its inference drops those heads): the rule is
+    ours (amt.h), this pins its CPU definition on cases whose answer is obvious."""
+    from oracle.notes import group_notes_onset_aware as dec
+    F = np.array([[0, 1, 1, 1, 0, 1, 1, 1, 1, 0]])
+    ON = np.array([[0, 1, 0, 0, 0, 0, 1, 1, 0, 0]])
+    OFF = np.array([[0, 0, 0, 0, 0, 0, 0, 0, 1, 0]])
+    assert dec(F, ON).tolist() == [[0, 1, 4], [0, 6, 9]]            # frame 5 sounds but no onset opened it
+    assert dec(F, ON, OFF).tolist() == [[0, 1, 4], [0, 6, 8]]       # the offset head ends the second note early
+    # re-strike inside a sounding note; an onset on a silent frame still sounds; open at the end
+    F = np.array([[1, 1, 1, 1, 1, 1], [0, 0, 0, 0, 0, 0]])
+    ON = np.array([[1, 0, 0, 1, 0, 0], [0, 0, 1, 1, 0, 1]])
+    assert dec(F, ON).tolist() == [[0, 0, 3], [0, 3, 6], [1, 2, 4], [1, 5, 6]]
+    assert dec(np.zeros((2, 5)), np.zeros((2, 5))).shape == (0, 3)
+
+
 def test_threshold_is_strict_float32_compare():
     p = np.array([[np.float32(0.1), np.nextafter(np.float32(0.1), np.float32(1))]], dtype=np.float32)
     assert onotes.threshold_roll(p, 0.1).tolist() == [[0.0, 1.0]]
