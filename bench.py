@@ -366,7 +366,7 @@ def main():
     W32 = (T + 31) // 32
     # two LANES: consecutive batches run on two streams, so the latency-bound recurrences of one batch (50-100 idle SMs)
     # overlap the tensor kernels of the other; results are bitwise those of a single stream (tests)
-    lane_streams = [torch.cuda.Stream(dev) for _ in range(2)] if args.lanes == 2 else [None]
+    lane_streams = pipeline.lane_streams(dev) if args.lanes == 2 else [None]
     rolls2 = [torch.empty(n_local, 88, W32, dtype=torch.int32, device=dev) for _ in range(2)]
     gather_dev = sharding.AsyncRollGather(n_local, R, T, dev)
     counter = {"batch": 0}
