@@ -301,7 +301,12 @@ static int forward(amt_model& m, const float* logmel, const float* chunk_max, fl
   }
 
   // ---- output heads ----
+  // The stacked head GEMM has frame | onset | offset in columns 0..87 | 88..175 | 176..263 (padded to 384).  When the
+  // caller asks for the frame head only (main.py's path), only the first 128-column n-tile is computed and transposed:
+  // the same accumulations, a third of the GEMM and of the transpose.
   int n_heads = 1;
+  const bool three = large && c.use_onset_offset && (onset != nullptr || offset != nullptr);
+  const int n_head_cols = three ? m.n_out_pad : 128;
   if (large && c.use_onset_offset) {
     if (precise) {
       STAGE("fc1", run_gemm(head_in, T_(m, "fc1.w"), F_(m, "fc1.b"), b.shared_f32, BT, m.H, m.D * km, m.H, 1, 1, s));
@@ -309,8 +314,8 @@ static int forward(amt_model& m, const float* logmel, const float* chunk_max, fl
     } else {
       STAGE("fc1", run_gemm(head_in, T_(m, "fc1.w"), F_(m, "fc1.b"), b.shared, BT, m.H, m.D, m.H, 1, 0, s));
     }
-    STAGE("heads", run_gemm(b.shared, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.H * km, m.n_out_pad, 0, 1, s));
-    n_heads = 3;
+    STAGE("heads", run_gemm(b.shared, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, n_head_cols, m.H * km, m.n_out_pad, 0, 1, s));
+    n_heads = three ? 3 : 1;
   } else {
     STAGE("heads", run_gemm(head_in, T_(m, "heads.w"), F_(m, "heads.b"), b.logits, BT, m.n_out_pad, m.D * km, m.n_out_pad, 0, 1, s));
   }
