@@ -35,7 +35,10 @@ struct FrontendDev {
   int n_mels, hop, rounds, fb_rows;          // fb_rows = sum of taps[]
   unsigned short taps[kMaxRounds], off[kMaxRounds];
 };
-constexpr int kPowFloats = 1025 + 1025 / 32 + 32;   // padded power spectrum: bin b at b + b/32, + 31 bins a zero-weight tap may touch
+// padded power spectrum of a frame: bin b at word b + b/32 (1057 words), + 32 zeroed words a zero-weight tap may touch;
+// it overwrites the frame's complex spectrum (32 x 33 float2 = 2112 words per warp)
+constexpr int kPowWords = 1025 + 1025 / 32 + 32;
+static_assert(kPowWords <= 2 * 32 * 33, "the power spectrum must fit the per-warp FFT scratch");
 
 // ---- 32-point in-register FFT (radix-2 DIF, output in bit-reversed order) ----
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -214,7 +217,7 @@ logmel_kernel(const float* __restrict__ wav, long long wav_stride, int n_samples
           pw[k2 + (k2 >> 5)] = qk[i];                      // (k = 512 writes the same value twice)
         }
       }
-      pw[1025 + 1025 / 32 + lane] = 0.0f;                  // words a zero-weight tap past bin 1024 may read: no NaN * 0
+      pw[kPowWords - 32 + lane] = 0.0f;                    // words a zero-weight tap past bin 1024 may read: no NaN * 0
       __syncwarp();
       // banded mel projection + dB: lane l of round r owns filter 32r + l
       const float* wrow = s_fb_w + lane;
