@@ -98,3 +98,24 @@ def test_product_package_never_touches_the_oracle_or_the_reference_tree():
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) and "/root/reference" not in src, f
     for f in ("bench.py", "__graft_entry__.py"):          # nothing the GPU box runs may read the reference tree
         assert "/root/reference" not in open(os.path.join(ROOT, f)).read()
+
+
+def test_deferred_logmel_host_logic_and_argument_checks():
+    """pipeline.DeferredLogMel (unfloored dB + per-chunk maxima): floored() is power_to_db's max - top_db clamp
+    (reference main.py:125) per chunk; the new C entry points refuse bad arguments without touching a GPU."""
+    import ctypes as C
+
+    import torch
+    from music_transcription_b200 import _lib, pipeline
+    mel = torch.tensor([[[[0.0, -50.0], [-90.0, -100.0]]], [[[-10.0, -95.0], [-200.0, -89.0]]]])      # (2, 1, 2, 2)
+    d = pipeline.DeferredLogMel(mel, torch.tensor([0.0, -10.0]), 80.0)
+    assert d.shape == mel.shape and d.device == mel.device
+    want = torch.tensor([[[[0.0, -50.0], [-80.0, -80.0]]], [[[-10.0, -90.0], [-90.0, -89.0]]]])
+    assert torch.equal(d.floored(), want)
+    L = _lib.lib()
+    assert L.amt_model_forward_db(None, None, None, 80.0, 1, 1, None, None, None, None, 0, None) == _lib.AMT_ERR_ARG
+    assert L.amt_onset_notes(None, None, None, 1, 88, 10, None, 0, None, None, 0, None) == _lib.AMT_ERR_ARG
+    assert L.amt_onset_notes_scratch_ints(88) == 88 and L.amt_onset_notes_scratch_ints(0) == 0
+    buf = (C.c_int32 * 4)()
+    st = L.amt_onset_notes(buf, buf, None, 1, 2000, 10, buf, 0, buf, buf, 4, None)                  # too many pitches
+    assert st == _lib.AMT_ERR_ARG and b"1024" in L.amt_last_error()
