@@ -13,7 +13,10 @@ offline, so its published algorithm is restated here.
 PARITY UNPINNED: the reference holds no tests or golden vectors for this stage
 and librosa cannot be run here.  The restatement is cross-checked against
 torchaudio's independent implementation (oracle/make_golden.py ->
-tests/golden/frontend_torchaudio.npz); they differ only by fp32-vs-fp64 FFT.
+tests/golden/frontend_torchaudio.npz; they differ only by fp32-vs-fp64 FFT) and
+against ``transformers.audio_utils``, HuggingFace's numpy port of librosa's
+filters.mel / melspectrogram / power_to_db (tests/test_oracle.py: filterbank
+3.7e-9, dB spectrogram 7.6e-6 max).
 """
 from __future__ import annotations
 

@@ -149,6 +149,30 @@ def test_frontend_oracle_vs_torchaudio_fixture():
     assert np.abs(mine - ofe.logmel_f64(y)).max() < 1e-4
 
 
+def test_frontend_oracle_vs_transformers_audio_utils():
+    """A second independent implementation of the librosa recipe: `transformers.audio_utils` (HuggingFace's numpy port of
+    librosa.filters.mel / melspectrogram / power_to_db, installed in this image -- librosa itself is not).  Same slaney
+    filterbank to 1e-8 and, with the arguments main.py:117-125 implies (periodic Hann 2048, hop 512, centred, constant
+    padding, power 2, amin 1e-10, top_db 80), the same dB spectrogram to 1e-4 dB on chord, noise and silence."""
+    au = pytest.importorskip("transformers.audio_utils")
+    from music_transcription_b200 import synth
+    from oracle import frontend as ofe
+    for n_mels in (320, 229, 64):
+        fb_hf = au.mel_filter_bank(num_frequency_bins=1025, num_mel_filters=n_mels, min_frequency=0.0, max_frequency=8000.0,
+                                   sampling_rate=16000, norm="slaney", mel_scale="slaney")
+        assert np.abs(fb_hf.T - ofe.mel_filterbank(n_mels=n_mels)).max() < 1e-7
+    fb_hf = au.mel_filter_bank(num_frequency_bins=1025, num_mel_filters=320, min_frequency=0.0, max_frequency=8000.0,
+                               sampling_rate=16000, norm="slaney", mel_scale="slaney")
+    win = au.window_function(2048, "hann", periodic=True)
+    rng = np.random.default_rng(3)
+    for y in (synth.piano_chord(0, n_samples=64000), rng.uniform(-1, 1, 30000).astype(np.float32), np.zeros(9000, np.float32)):
+        S = au.spectrogram(y.astype(np.float64), win, frame_length=2048, hop_length=512, fft_length=2048, power=2.0, center=True,
+                           pad_mode="constant", onesided=True, mel_filters=fb_hf, mel_floor=1e-10, log_mel="dB", reference=1.0,
+                           min_value=1e-10, db_range=80.0)
+        ref = ofe.logmel(y)
+        assert S.shape == ref.shape and np.abs(S - ref).max() < 1e-4, np.abs(S - ref).max()
+
+
 def test_frontend_filterbank_properties():
     fb = ofe.mel_filterbank()
     assert fb.shape == (320, 1025) and fb.dtype == np.float32
