@@ -293,7 +293,10 @@ int run_split3(const void* x, int in_f32, void* out, long long rows, int K, cuda
 // ----------------------------------------------------------------------------
 constexpr int kLnMaxVec = 18;   // D <= 2304
 
-template <bool SPLIT>
+// NV = float4 per lane the row needs (D / 128) when it is one of the model's widths (1536 -> 12, 768 -> 6, 384 -> 3:
+// hidden 512 / 256 / 128), else the generic bound: sizing the register row to the real width (48 instead of 72 registers
+// at D = 1536) lets a third CTA share the SM.
+template <bool SPLIT, int NV>
 __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             __nv_bfloat16* __restrict__ out, long long rows, int D, float eps) {
@@ -303,10 +306,10 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   const int nvec = D >> 7;                       // float4 per lane
   const float4* pa = reinterpret_cast<const float4*>(a + row * D);
   const float4* pb = reinterpret_cast<const float4*>(b + row * D);
-  float4 v[kLnMaxVec];
+  float4 v[NV];
   float sum = 0.0f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (i < nvec) {
       const float4 x = __ldg(pa + i * 32 + lane), y = __ldg(pb + i * 32 + lane);
       v[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   const float mean = sum / D;
   float sq = 0.0f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (i < nvec) {
       const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
       sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   const float4* pg = reinterpret_cast<const float4*>(gamma);
   const float4* pbt = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (i < nvec) {
       const float4 g = __ldg(pg + i * 32 + lane), bt = __ldg(pbt + i * 32 + lane);
       const float y0 = (v[i].x - mean) * rstd * g.x + bt.x, y1 = (v[i].y - mean) * rstd * g.y + bt.y;
@@ -350,8 +353,19 @@ int run_add_layernorm(const float* a, const float* b, const float* gamma, const 
                       int D, float eps, int split, cudaStream_t stream) {
   AMT_REQUIRE(D % 128 == 0 && D <= 128 * kLnMaxVec, "layernorm: D (%d) must be a multiple of 128 and <= %d", D, 128 * kLnMaxVec);
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  if (split) add_layernorm_kernel<true><<<grid, 256, 0, stream>>>(a, b, gamma, beta, static_cast<__nv_bfloat16*>(out), rows, D, eps);
-  else add_layernorm_kernel<false><<<grid, 256, 0, stream>>>(a, b, gamma, beta, static_cast<__nv_bfloat16*>(out), rows, D, eps);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+#define AMT_LN_LAUNCH(NV_)                                                                                      \
+  do {                                                                                                          \
+    if (split) add_layernorm_kernel<true, NV_><<<grid, 256, 0, stream>>>(a, b, gamma, beta, o, rows, D, eps);   \
+    else add_layernorm_kernel<false, NV_><<<grid, 256, 0, stream>>>(a, b, gamma, beta, o, rows, D, eps);        \
+  } while (0)
+  switch (D >> 7) {
+    case 3: AMT_LN_LAUNCH(3); break;
+    case 6: AMT_LN_LAUNCH(6); break;
+    case 12: AMT_LN_LAUNCH(12); break;
+    default: AMT_LN_LAUNCH(kLnMaxVec); break;
+  }
+#undef AMT_LN_LAUNCH
   AMT_CHECK_LAUNCH();
   return 0;
 }
