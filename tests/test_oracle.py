@@ -101,6 +101,30 @@ def test_onset_aware_decoding_rule_on_hand_cases():
     assert dec(np.zeros((2, 5)), np.zeros((2, 5))).shape == (0, 3)
 
 
+def test_onset_aware_decoding_loop_equals_a_vectorised_restatement():
+    """The loop in oracle/notes.py is the definition; the same rule written with array operations (starts = rising onset
+    edges, boundaries = silence | start | offset, each start paired with the next boundary by searchsorted) must give the
+    same notes on random rolls -- two independent writings of the rule the GPU kernel is held to."""
+    from oracle.notes import group_notes_onset_aware as dec
+    rng = np.random.default_rng(11)
+    for trial in range(20):
+        P, N = int(rng.integers(1, 6)), int(rng.integers(1, 300))
+        F = rng.random((P, N)) < rng.uniform(0.1, 0.9)
+        ON = rng.random((P, N)) < rng.uniform(0.02, 0.6)
+        OFF = (rng.random((P, N)) < rng.uniform(0.0, 0.3)) if trial % 2 else None
+        rows = []
+        for p in range(P):
+            prev = np.concatenate([[False], ON[p, :-1]])
+            S = ON[p] & ~prev
+            B = ~(F[p] | ON[p]) | S | (OFF[p] if OFF is not None else False)
+            starts, bounds = np.flatnonzero(S), np.flatnonzero(B)
+            k = np.searchsorted(bounds, starts, side="right")             # first boundary strictly after the start
+            ends = np.where(k < len(bounds), bounds[np.minimum(k, len(bounds) - 1)] if len(bounds) else N, N)
+            rows += [(p, int(a), int(b)) for a, b in zip(starts, ends)]
+        want = np.asarray(rows, dtype=np.int32).reshape(-1, 3)
+        assert np.array_equal(dec(F, ON, OFF), want), trial
+
+
 def test_threshold_is_strict_float32_compare():
     p = np.array([[np.float32(0.1), np.nextafter(np.float32(0.1), np.float32(1))]], dtype=np.float32)
     assert onotes.threshold_roll(p, 0.1).tolist() == [[0.0, 1.0]]
